@@ -1,0 +1,106 @@
+"""ctypes binding of the C ABI declared in ``include/mpr_b200.h``.
+
+The shared library is the product: if it is missing, or the device is not a B200-class (sm_100) GPU, every entry
+point raises — there is no eager / CPU fallback anywhere in this package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libmpr_b200.so")
+
+MPR_MAX_KK = 32
+SRC_F32, SRC_F16, SRC_BF16 = 0, 1, 2
+
+EXPORTS = [
+    "mpr_abi_version", "mpr_create", "mpr_destroy", "mpr_last_error", "mpr_device_error", "mpr_bank_build",
+    "mpr_search_workspace_bytes", "mpr_search_topk", "mpr_merge_topk", "mpr_prompt_gather", "mpr_debug_scores",
+    "mpr_search_plan",
+]
+
+_lib: Optional[C.CDLL] = None
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """Load libmpr_b200.so (built by ``__graft_entry__.build()`` / ``csrc/build.py``) and declare signatures."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeError(
+            f"{LIB_PATH} not found: build it with `python -m multimodalpromptretrieval_b200.csrc.build` "
+            "(this package has no fallback path)")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, sz = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
+    lib.mpr_abi_version.restype = i32
+    lib.mpr_abi_version.argtypes = []
+    lib.mpr_create.restype = i32
+    lib.mpr_create.argtypes = [i32, C.POINTER(vp)]
+    lib.mpr_destroy.restype = i32
+    lib.mpr_destroy.argtypes = [vp]
+    lib.mpr_last_error.restype = C.c_char_p
+    lib.mpr_last_error.argtypes = [vp]
+    lib.mpr_device_error.restype = i32
+    lib.mpr_device_error.argtypes = [vp, C.POINTER(i32)]
+    lib.mpr_bank_build.restype = i32
+    lib.mpr_bank_build.argtypes = [vp, vp, i32, vp, i32, i32, i64, i32, vp, vp, vp]
+    lib.mpr_search_workspace_bytes.restype = sz
+    lib.mpr_search_workspace_bytes.argtypes = [vp, i32, i64, i32, i32]
+    lib.mpr_search_topk.restype = i32
+    lib.mpr_search_topk.argtypes = [vp, vp, i32, vp, vp, i64, i64, i32, i32, vp, vp, vp, vp, sz, vp]
+    lib.mpr_merge_topk.restype = i32
+    lib.mpr_merge_topk.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp]
+    lib.mpr_prompt_gather.restype = i32
+    lib.mpr_prompt_gather.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32,
+                                      vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.mpr_debug_scores.restype = i32
+    lib.mpr_debug_scores.argtypes = [vp, vp, i32, vp, vp, i64, i32, vp, vp, sz, vp]
+    lib.mpr_search_plan.restype = i32
+    lib.mpr_search_plan.argtypes = [vp, i32, i64, i32, i32] + [C.POINTER(i32)] * 5
+    _lib = lib
+    return lib
+
+
+class Handle:
+    """Owns one ``mpr_handle_t`` (one per process and device)."""
+
+    def __init__(self, device: int):
+        self.lib = load()
+        self._h = C.c_void_p()
+        rc = self.lib.mpr_create(int(device), C.byref(self._h))
+        if rc != 0:
+            msg = self.lib.mpr_last_error(None)
+            raise NativeError(f"mpr_create(device={device}) failed ({rc}): {msg.decode() if msg else '?'}")
+        self.device = int(device)
+
+    @property
+    def ptr(self) -> C.c_void_p:
+        return self._h
+
+    def check(self, rc: int, what: str) -> None:
+        if rc != 0:
+            msg = self.lib.mpr_last_error(self._h)
+            raise NativeError(f"{what} failed ({rc}): {msg.decode() if msg else '?'}")
+
+    def device_error(self) -> int:
+        code = C.c_int(0)
+        self.check(self.lib.mpr_device_error(self._h, C.byref(code)), "mpr_device_error")
+        return code.value
+
+    def close(self) -> None:
+        if self._h:
+            self.lib.mpr_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

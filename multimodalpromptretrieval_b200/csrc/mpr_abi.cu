@@ -1,0 +1,328 @@
+// C-ABI entry points (include/mpr_b200.h): argument validation, launch planning, TMA descriptor encoding and
+// kernel launches.  No device synchronisation, no persistent device allocations beyond one error word.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+
+#include "../../include/mpr_b200.h"
+#include "bank_build.cuh"
+#include "merge_topk.cuh"
+#include "prompt_gather.cuh"
+#include "scan_topk.cuh"
+
+using namespace mpr;
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct mpr_context {
+    int device = -1;
+    int num_sms = 0;
+    int* d_err = nullptr;
+    PFN_encodeTiled encode = nullptr;
+    char err[512] = {0};
+};
+
+static thread_local char g_err[512] = "";
+
+static int fail(mpr_context* h, int code, const char* fmt, ...) {
+    char* dst = h ? h->err : g_err;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(dst, 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(h, call)                                                                              \
+    do {                                                                                               \
+        cudaError_t e__ = (call);                                                                      \
+        if (e__ != cudaSuccess)                                                                        \
+            return fail(h, MPR_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static inline int pow2_ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+// ------------------------------------------------------------------------------------------------ planning
+struct ScanPlan {
+    int n_chunks, q_tile, q_box_rows, n_qtiles, n_splits, n_tiles, n_stages, kk_pad;
+    uint32_t smem_bytes;
+};
+
+static int make_plan(mpr_context* h, int b, int64_t n_local, int d, int kk, ScanPlan* pl) {
+    if (b < 1) return fail(h, MPR_EINVAL, "b must be >= 1 (got %d)", b);
+    if (n_local < 1 || n_local >= (1ll << 31) - kTileRows)
+        return fail(h, MPR_EINVAL, "n_local out of range (got %lld)", static_cast<long long>(n_local));
+    if (d < 64 || d > 4096 || d % 64 != 0) return fail(h, MPR_EINVAL, "d must be a multiple of 64 in [64, 4096] (got %d)", d);
+    if (kk < 1 || kk > MPR_MAX_KK) return fail(h, MPR_EINVAL, "k + skip must be in [1, %d] (got %d)", MPR_MAX_KK, kk);
+
+    pl->n_chunks = d / kChunkK;
+    int q_tile_max = 128;
+    while (q_tile_max > 8 && static_cast<long long>(q_tile_max) * d * 2 > 131072) q_tile_max >>= 1;
+    if (b <= q_tile_max) {
+        pl->q_tile = b;
+        pl->n_qtiles = 1;
+        pl->q_box_rows = pow2_ceil(b) < 8 ? 8 : pow2_ceil(b);
+    } else {
+        pl->q_tile = q_tile_max;
+        pl->n_qtiles = (b + q_tile_max - 1) / q_tile_max;
+        pl->q_box_rows = q_tile_max;
+    }
+    pl->kk_pad = pow2_ceil(kk);
+    pl->n_tiles = static_cast<int>((n_local + kTileRows - 1) / kTileRows);
+    // items = n_splits * n_qtiles should be a whole number of waves over the SMs
+    const int g = std::gcd(h->num_sms, pl->n_qtiles);
+    pl->n_splits = h->num_sms / g;
+    if (pl->n_splits > pl->n_tiles) pl->n_splits = pl->n_tiles;
+    if (pl->n_splits < 1) pl->n_splits = 1;
+
+    const ScanSmemLayout fixed = scan_smem_layout(pl->n_chunks, pl->q_box_rows, pl->kk_pad, 0);
+    const int avail = kMaxSmem - 1024 - static_cast<int>(fixed.total);
+    int stages = avail / kStageBytes;
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (stages < 2) return fail(h, MPR_EINVAL, "shape does not fit shared memory (d=%d, kk=%d)", d, kk);
+    pl->n_stages = stages;
+    pl->smem_bytes = scan_smem_layout(pl->n_chunks, pl->q_box_rows, pl->kk_pad, stages).total + 1024u;
+    return MPR_OK;
+}
+
+static int encode_2d(mpr_context* h, CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols,
+                     uint32_t box_rows) {
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {cols * 2};
+    cuuint32_t box[2] = {kChunkK, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = h->encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail(h, MPR_ECUDA, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu box_rows=%u", static_cast<int>(r),
+                    static_cast<unsigned long long>(rows), static_cast<unsigned long long>(cols), box_rows);
+    return MPR_OK;
+}
+
+template <bool kDump>
+static int launch_scan(mpr_context* h, const ScanPlan& pl, const uint16_t* q, int b, const uint16_t* bank,
+                       const float* bias, int64_t n_local, int64_t idx_base, int d, int kk, uint64_t* part_keys,
+                       float* dump, cudaStream_t st) {
+    CUtensorMap tq, tb;
+    int rc = encode_2d(h, &tq, q, static_cast<uint64_t>(b), static_cast<uint64_t>(d), pl.q_box_rows);
+    if (rc) return rc;
+    rc = encode_2d(h, &tb, bank, static_cast<uint64_t>(n_local), static_cast<uint64_t>(d), kTileRows);
+    if (rc) return rc;
+
+    ScanParams p;
+    p.b_total = b;
+    p.n_local = static_cast<int>(n_local);
+    p.n_chunks = pl.n_chunks;
+    p.kk = kk;
+    p.kk_pad = pl.kk_pad;
+    p.q_tile = pl.q_tile;
+    p.q_box_rows = pl.q_box_rows;
+    p.n_qtiles = pl.n_qtiles;
+    p.n_splits = pl.n_splits;
+    p.n_tiles = pl.n_tiles;
+    p.n_stages = pl.n_stages;
+    p.idx_base = static_cast<uint32_t>(idx_base);
+    p.bank_policy = pl.n_qtiles == 1 ? ptx::kEvictFirst : ptx::kEvictNormal;
+    p.bias = bias;
+    p.part_keys = part_keys;
+    p.dump = dump;
+    p.err = h->d_err;
+
+    const dim3 grid(pl.n_splits * pl.n_qtiles);
+    scan_topk_kernel<kDump><<<grid, kScanThreads, pl.smem_bytes, st>>>(tq, tb, p);
+    CUDA_TRY(h, cudaGetLastError());
+    return MPR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ exports
+extern "C" {
+
+int mpr_abi_version(void) { return MPR_ABI_VERSION; }
+
+const char* mpr_last_error(mpr_handle_t h) { return h ? h->err : g_err; }
+
+int mpr_create(int device, mpr_handle_t* out) {
+    if (!out) return fail(nullptr, MPR_EINVAL, "out is null");
+    *out = nullptr;
+    CUDA_TRY(nullptr, cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(nullptr, cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(nullptr, MPR_EARCH, "device %d is sm_%d%d; this library is sm_100a-only (no fallback path)", device,
+                    prop.major, prop.minor);
+    mpr_context* h = new mpr_context();
+    h->device = device;
+    h->num_sms = prop.multiProcessorCount;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+        delete h;
+        return fail(nullptr, MPR_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
+    }
+    h->encode = reinterpret_cast<PFN_encodeTiled>(fn);
+    e = cudaMalloc(&h->d_err, sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(h->d_err, 0, sizeof(int));
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(scan_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(scan_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (e != cudaSuccess) {
+        fail(nullptr, MPR_ECUDA, "handle setup failed: %s", cudaGetErrorString(e));
+        if (h->d_err) cudaFree(h->d_err);
+        delete h;
+        return MPR_ECUDA;
+    }
+    *out = h;
+    return MPR_OK;
+}
+
+int mpr_destroy(mpr_handle_t h) {
+    if (!h) return MPR_OK;
+    if (h->d_err) cudaFree(h->d_err);
+    delete h;
+    return MPR_OK;
+}
+
+int mpr_device_error(mpr_handle_t h, int* code) {
+    if (!h || !code) return fail(h, MPR_EINVAL, "null argument");
+    CUDA_TRY(h, cudaMemcpy(code, h->d_err, sizeof(int), cudaMemcpyDeviceToHost));
+    if (*code != 0) CUDA_TRY(h, cudaMemset(h->d_err, 0, sizeof(int)));
+    return MPR_OK;
+}
+
+int mpr_bank_build(mpr_handle_t h, const void* src0, int d0, const void* src1, int d1, int src_dtype, int64_t n,
+                   int normalise, uint16_t* out_bf16, float* out_bias, void* stream) {
+    if (!h) return fail(nullptr, MPR_EINVAL, "null handle");
+    if (n == 0) return MPR_OK;
+    if (n < 0 || !src0 || !out_bf16) return fail(h, MPR_EINVAL, "null pointer or negative n");
+    if (!src1) d1 = 0;
+    const int d = d0 + d1;
+    if (d0 < 8 || d0 % 8 || d1 % 8 || d % 64 || d > 2048)
+        return fail(h, MPR_EINVAL, "d0=%d d1=%d: parts must be multiples of 8, total a multiple of 64 and <= 2048", d0, d1);
+    if (src_dtype < MPR_SRC_F32 || src_dtype > MPR_SRC_BF16) return fail(h, MPR_EINVAL, "bad src_dtype %d", src_dtype);
+    if (!aligned16(src0) || !aligned16(src1) || !aligned16(out_bf16))
+        return fail(h, MPR_EINVAL, "pointers must be 16-byte aligned");
+    const int threads = 256, rows_per_block = threads / 32;
+    long long blocks = (n + rows_per_block - 1) / rows_per_block;
+    const long long cap = static_cast<long long>(h->num_sms) * 16;   // grid-stride over rows beyond this
+    if (blocks > cap) blocks = cap;
+    bank_build_kernel<<<static_cast<unsigned>(blocks), threads, 0, static_cast<cudaStream_t>(stream)>>>(
+        src0, d0, src1, d1, src_dtype, n, normalise, out_bf16, out_bias);
+    CUDA_TRY(h, cudaGetLastError());
+    return MPR_OK;
+}
+
+size_t mpr_search_workspace_bytes(mpr_handle_t h, int b, int64_t n_local, int d, int kk) {
+    if (!h) return 0;
+    ScanPlan pl;
+    if (make_plan(h, b, n_local, d, kk, &pl)) return 0;
+    return static_cast<size_t>(pl.n_splits) * b * kk * sizeof(uint64_t);
+}
+
+int mpr_search_plan(mpr_handle_t h, int b, int64_t n_local, int d, int kk, int* n_ctas, int* n_splits, int* n_qtiles,
+                    int* n_stages, int* smem_bytes) {
+    if (!h) return fail(nullptr, MPR_EINVAL, "null handle");
+    ScanPlan pl;
+    int rc = make_plan(h, b, n_local, d, kk, &pl);
+    if (rc) return rc;
+    if (n_ctas) *n_ctas = pl.n_splits * pl.n_qtiles;
+    if (n_splits) *n_splits = pl.n_splits;
+    if (n_qtiles) *n_qtiles = pl.n_qtiles;
+    if (n_stages) *n_stages = pl.n_stages;
+    if (smem_bytes) *smem_bytes = static_cast<int>(pl.smem_bytes);
+    return MPR_OK;
+}
+
+int mpr_search_topk(mpr_handle_t h, const uint16_t* q, int b, const uint16_t* bank, const float* bias, int64_t n_local,
+                    int64_t idx_base, int d, int kk, uint64_t* out_keys, float* out_score, int32_t* out_idx,
+                    void* workspace, size_t workspace_bytes, void* stream) {
+    if (!h) return fail(nullptr, MPR_EINVAL, "null handle");
+    if (b == 0) return MPR_OK;
+    if (!q || !bank || !bias || !workspace) return fail(h, MPR_EINVAL, "null pointer");
+    if (!aligned16(q) || !aligned16(bank) || !aligned16(workspace))
+        return fail(h, MPR_EINVAL, "q, bank and workspace must be 16-byte aligned");
+    if (idx_base < 0 || idx_base + n_local >= 0xFFFFFFFFll) return fail(h, MPR_EINVAL, "global row index exceeds 32 bits");
+    ScanPlan pl;
+    int rc = make_plan(h, b, n_local, d, kk, &pl);
+    if (rc) return rc;
+    const size_t need = static_cast<size_t>(pl.n_splits) * b * kk * sizeof(uint64_t);
+    if (workspace_bytes < need)
+        return fail(h, MPR_EWORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, need);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    uint64_t* part = static_cast<uint64_t*>(workspace);
+    rc = launch_scan<false>(h, pl, q, b, bank, bias, n_local, idx_base, d, kk, part, nullptr, st);
+    if (rc) return rc;
+    const int warps_per_block = 4;
+    merge_topk_kernel<<<(b + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(
+        part, pl.n_splits, static_cast<long long>(b) * kk, b, kk, out_keys, out_score, out_idx);
+    CUDA_TRY(h, cudaGetLastError());
+    return MPR_OK;
+}
+
+int mpr_merge_topk(mpr_handle_t h, const uint64_t* in_keys, int n_lists, int b, int kk, uint64_t* out_keys,
+                   float* out_score, int32_t* out_idx, void* stream) {
+    if (!h) return fail(nullptr, MPR_EINVAL, "null handle");
+    if (b == 0) return MPR_OK;
+    if (!in_keys || n_lists < 1 || b < 0) return fail(h, MPR_EINVAL, "bad arguments");
+    if (kk < 1 || kk > MPR_MAX_KK) return fail(h, MPR_EINVAL, "k + skip must be in [1, %d] (got %d)", MPR_MAX_KK, kk);
+    const int warps_per_block = 4;
+    merge_topk_kernel<<<(b + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0,
+                        static_cast<cudaStream_t>(stream)>>>(in_keys, n_lists, static_cast<long long>(b) * kk, b, kk,
+                                                             out_keys, out_score, out_idx);
+    CUDA_TRY(h, cudaGetLastError());
+    return MPR_OK;
+}
+
+int mpr_prompt_gather(mpr_handle_t h, const int32_t* idx, int b, int kk, int skip, const int32_t* answer_id,
+                      const uint8_t* bucket_lut, const int32_t* prefix_ids, const int32_t* prefix_off,
+                      const int32_t* seg_ids, const int32_t* seg_off, int use_quantifier, int pad_id, int eos_id,
+                      int max_len, int out_stride, int64_t* input_ids, int64_t* attention_mask, int32_t* out_len,
+                      int32_t* maj_answer, int32_t* maj_count, int32_t* bucket, int32_t* ret_answer, void* stream) {
+    if (!h) return fail(nullptr, MPR_EINVAL, "null handle");
+    if (b == 0) return MPR_OK;
+    if (!idx || !answer_id || !bucket_lut || !prefix_ids || !prefix_off || !seg_ids || !seg_off || !input_ids ||
+        !attention_mask || !out_len || !maj_answer || !maj_count || !bucket)
+        return fail(h, MPR_EINVAL, "null pointer");
+    if (kk < 1 || kk > MPR_MAX_KK || skip < 0 || skip >= kk)
+        return fail(h, MPR_EINVAL, "need 1 <= kk <= %d and 0 <= skip < kk (kk=%d skip=%d)", MPR_MAX_KK, kk, skip);
+    if (max_len < 1 || out_stride < 1) return fail(h, MPR_EINVAL, "max_len and out_stride must be >= 1");
+    PromptParams p;
+    p.idx = idx; p.b = b; p.kk = kk; p.skip = skip;
+    p.answer_id = answer_id; p.bucket_lut = bucket_lut;
+    p.prefix_ids = prefix_ids; p.prefix_off = prefix_off; p.seg_ids = seg_ids; p.seg_off = seg_off;
+    p.use_quantifier = use_quantifier; p.pad_id = pad_id; p.eos_id = eos_id;
+    p.max_len = max_len; p.out_stride = out_stride;
+    p.input_ids = reinterpret_cast<long long*>(input_ids);
+    p.attention_mask = reinterpret_cast<long long*>(attention_mask);
+    p.out_len = out_len; p.maj_answer = maj_answer; p.maj_count = maj_count; p.bucket = bucket;
+    p.ret_answer = ret_answer;
+    const int warps_per_block = 4;
+    prompt_gather_kernel<<<(b + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0,
+                           static_cast<cudaStream_t>(stream)>>>(p);
+    CUDA_TRY(h, cudaGetLastError());
+    return MPR_OK;
+}
+
+int mpr_debug_scores(mpr_handle_t h, const uint16_t* q, int b, const uint16_t* bank, const float* bias,
+                     int64_t n_local, int d, float* scores, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!h) return fail(nullptr, MPR_EINVAL, "null handle");
+    if (!q || !bank || !bias || !scores || !workspace) return fail(h, MPR_EINVAL, "null pointer");
+    ScanPlan pl;
+    int rc = make_plan(h, b, n_local, d, 1, &pl);
+    if (rc) return rc;
+    const size_t need = static_cast<size_t>(pl.n_splits) * b * sizeof(uint64_t);
+    if (workspace_bytes < need) return fail(h, MPR_EWORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, need);
+    return launch_scan<true>(h, pl, q, b, bank, bias, n_local, 0, d, 1, static_cast<uint64_t*>(workspace), scores,
+                             static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

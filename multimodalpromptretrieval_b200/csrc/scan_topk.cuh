@@ -1,0 +1,307 @@
+// Kernel 2 — fused bank scan: bf16 similarity GEMM on tcgen05 (accumulators in TMEM, operands staged by
+// TMA through an mbarrier ring) whose epilogue keeps a streaming per-query top-k.  The [B, N] score matrix
+// of the reference (torch.cdist -> torch.argsort, /root/reference/dataset/VQAFeatureDataset.py:192-197)
+// is never written.
+//
+// score[q, r] = <q, bank[r]> + bias[r],  bias[r] = -0.5 * ||bank[r]||^2   (so argmax score == argmin L2 distance)
+//
+// Orientation: queries are the MMA M dimension (one TMEM lane per query), bank rows the N dimension
+// (one TMEM column per row).  Each epilogue thread therefore owns ONE query and walks its lane's columns in
+// ascending row order: the common case per score is one FADD + a share of a max and a vote; only scores that
+// beat the query's current k-th best take the (warp-cooperative) insert path.
+//
+// Work decomposition: item = (bank split s, q-tile t); one CTA per item, blockIdx.x = s * n_qtiles + t, so the
+// CTAs resident at the same time share a bank range and all but the first read of it hit L2.  The q-tile
+// (<= 128 queries, <= 128 KiB) is loaded once and stays resident in shared memory; only the bank streams.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+// warps 2..5 = epilogue (warp w reads TMEM lanes 32*(w%4)...).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <math_constants.h>
+
+#include "ptx.cuh"
+#include "topk_key.cuh"
+
+namespace mpr {
+
+constexpr int kTileRows = 128;                // bank rows per accumulator tile (UMMA N)
+constexpr int kUmmaM = 128;                   // TMEM lanes = query slots per CTA
+constexpr int kChunkK = 64;                   // bf16 per 128-byte swizzled row
+constexpr int kStageBytes = kTileRows * 128;  // one bank K-chunk: 128 rows x 128 B = 16 KiB
+constexpr int kAccBufs = 4;                   // TMEM accumulator ring: 4 x 128 columns
+constexpr int kTmemCols = 512;
+constexpr int kScanThreads = 192;
+constexpr int kMaxStages = 12;
+constexpr int kMaxSmem = 232448;              // 227 KiB opt-in limit per CTA on sm_100
+constexpr int kMaxKK = 32;
+
+struct ScanParams {
+    int b_total;       // queries in the batch
+    int n_local;       // bank rows in this shard
+    int n_chunks;      // D / 64
+    int kk;            // list length (k + skip), 1..32
+    int kk_pad;        // next power of two >= kk
+    int q_tile;        // queries per q-tile
+    int q_box_rows;    // rows of the Q TMA box (multiple of 8, >= valid rows of any q-tile)
+    int n_qtiles;
+    int n_splits;
+    int n_tiles;       // ceil(n_local / 128)
+    int n_stages;
+    uint32_t idx_base; // global row index of this shard's row 0
+    uint64_t bank_policy;
+    const float* bias;     // [n_local]
+    uint64_t* part_keys;   // [n_splits][b_total][kk]
+    float* dump;           // debug: [b_total][n_local] scores, or nullptr
+    int* err;              // device word that receives the code of a starved barrier
+};
+
+struct ScanSmemLayout {
+    uint32_t q_off, stage_off, list_off, bias_off, bar_off, total;
+};
+
+__host__ __device__ inline ScanSmemLayout scan_smem_layout(int n_chunks, int q_box_rows, int kk_pad, int n_stages) {
+    ScanSmemLayout l;
+    l.q_off = 0;
+    l.stage_off = static_cast<uint32_t>(n_chunks) * q_box_rows * 128u;          // multiple of 1024
+    l.list_off = l.stage_off + static_cast<uint32_t>(n_stages) * kStageBytes;
+    l.bias_off = l.list_off + static_cast<uint32_t>(kUmmaM) * kk_pad * 8u;
+    l.bar_off = l.bias_off + kAccBufs * kTileRows * 4u;
+    l.total = l.bar_off + (1 + 2 * kMaxStages + 2 * kAccBufs) * 8u + 16u;
+    return l;
+}
+
+// Barrier error codes (ScanParams::err)
+enum : int { kErrQFull = 101, kErrEmpty = 102, kErrFull = 103, kErrTmemEmpty = 104, kErrTmemFull = 105 };
+
+template <bool kDump>
+__global__ void __launch_bounds__(kScanThreads, 1)
+scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_bank,
+                 const ScanParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+    const uint32_t base = (raw_addr + 1023u) & ~1023u;   // SWIZZLE_128B atoms need 1024-byte alignment
+    uint8_t* smem = smem_raw + (base - raw_addr);
+
+    const ScanSmemLayout lay = scan_smem_layout(p.n_chunks, p.q_box_rows, p.kk_pad, p.n_stages);
+    const uint32_t q_smem = base + lay.q_off;
+    const uint32_t stage_smem = base + lay.stage_off;
+    uint64_t* lists = reinterpret_cast<uint64_t*>(smem + lay.list_off);
+    float* bias_s = reinterpret_cast<float*>(smem + lay.bias_off);
+    const uint32_t bar_base = base + lay.bar_off;
+    const uint32_t bar_q = bar_base;
+    auto bar_full = [&](int s) { return bar_base + 8u + 8u * s; };
+    auto bar_empty = [&](int s) { return bar_base + 8u + 8u * (kMaxStages + s); };
+    auto bar_tfull = [&](int b) { return bar_base + 8u + 8u * (2 * kMaxStages + b); };
+    auto bar_tempty = [&](int b) { return bar_base + 8u + 8u * (2 * kMaxStages + kAccBufs + b); };
+    volatile uint32_t* tmem_slot =
+        reinterpret_cast<volatile uint32_t*>(smem + lay.bar_off + (1 + 2 * kMaxStages + 2 * kAccBufs) * 8u);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    // ---- which item is this CTA's
+    const int item = blockIdx.x;
+    const int split = item / p.n_qtiles;
+    const int qt = item - split * p.n_qtiles;
+    const int q0 = qt * p.q_tile;
+    const int q_valid = min(p.q_tile, p.b_total - q0);
+    const int tile_begin = static_cast<int>(static_cast<long long>(split) * p.n_tiles / p.n_splits);
+    const int tile_end = static_cast<int>(static_cast<long long>(split + 1) * p.n_tiles / p.n_splits);
+    const int my_tiles = tile_end - tile_begin;
+
+    // ---- one-time setup
+    if (threadIdx.x == 0) {
+        ptx::mbar_init(bar_q, 1);
+        for (int s = 0; s < p.n_stages; ++s) {
+            ptx::mbar_init(bar_full(s), 1);
+            ptx::mbar_init(bar_empty(s), 1);
+        }
+        for (int b = 0; b < kAccBufs; ++b) {
+            ptx::mbar_init(bar_tfull(b), 1);
+            ptx::mbar_init(bar_tempty(b), 4);   // one arrive per epilogue warp
+        }
+        ptx::fence_mbar_init();
+        ptx::prefetch_tensormap(&tmap_q);
+        ptx::prefetch_tensormap(&tmap_bank);
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(ptx::smem_u32(const_cast<uint32_t*>(tmem_slot)), kTmemCols);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // =========================== TMA producer ===========================
+        if (lane == 0) {
+            // resident q-tile: one 128-byte-wide slab per K-chunk
+            const uint32_t slab_bytes = static_cast<uint32_t>(p.q_box_rows) * 128u;
+            ptx::mbar_arrive_expect_tx(bar_q, slab_bytes * p.n_chunks);
+            for (int j = 0; j < p.n_chunks; ++j)
+                ptx::tma_load_2d(q_smem + j * slab_bytes, &tmap_q, bar_q, j * kChunkK, q0, ptx::kEvictLast);
+            // streamed bank
+            int s = 0;
+            uint32_t ph = 0;
+            for (int t = tile_begin; t < tile_end; ++t) {
+                for (int j = 0; j < p.n_chunks; ++j) {
+                    ptx::mbar_wait(bar_empty(s), ph ^ 1u, p.err, kErrEmpty);
+                    ptx::mbar_arrive_expect_tx(bar_full(s), kStageBytes);
+                    ptx::tma_load_2d(stage_smem + s * kStageBytes, &tmap_bank, bar_full(s), j * kChunkK,
+                                     t * kTileRows, p.bank_policy);
+                    if (++s == p.n_stages) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // =========================== MMA issuer ===========================
+        if (lane == 0) {
+            constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(kUmmaM, kTileRows);
+            const uint32_t slab_bytes = static_cast<uint32_t>(p.q_box_rows) * 128u;
+            ptx::mbar_wait(bar_q, 0, p.err, kErrQFull);
+            int s = 0;
+            uint32_t ph = 0;
+            for (int lt = 0; lt < my_tiles; ++lt) {
+                const int buf = lt & (kAccBufs - 1);
+                const uint32_t bph = (lt / kAccBufs) & 1u;
+                ptx::mbar_wait(bar_tempty(buf), bph ^ 1u, p.err, kErrTmemEmpty);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * kTileRows;
+                for (int j = 0; j < p.n_chunks; ++j) {
+                    ptx::mbar_wait(bar_full(s), ph, p.err, kErrFull);
+                    ptx::tc_fence_after();
+                    const uint32_t a_addr = q_smem + j * slab_bytes;
+                    const uint32_t b_addr = stage_smem + s * kStageBytes;
+#pragma unroll
+                    for (int k = 0; k < kChunkK / 16; ++k) {
+                        const uint64_t da = ptx::make_kmajor_sw128_desc(a_addr + k * 32);
+                        const uint64_t db = ptx::make_kmajor_sw128_desc(b_addr + k * 32);
+                        ptx::umma_bf16_ss(d_tmem, da, db, idesc, (j | k) != 0 ? 1u : 0u);
+                    }
+                    ptx::umma_commit(bar_empty(s));          // smem slot reusable once these MMAs retire
+                    if (++s == p.n_stages) { s = 0; ph ^= 1u; }
+                }
+                ptx::umma_commit(bar_tfull(buf));            // accumulator tile complete
+            }
+        }
+    } else {
+        // =========================== epilogue: streaming top-k ===========================
+        const int quad = warp & 3;                     // TMEM lane quadrant this warp may read
+        const int row = quad * 32 + lane;              // query slot (TMEM lane) owned by this thread
+        const bool valid = row < q_valid;
+        const bool warp_has_work = quad * 32 < q_valid;
+        const int ep_tid = (warp - 2) * 32 + lane;     // 0..127, used to stage the bias tile
+        const int kk = p.kk;
+        const int kk_pad = p.kk_pad;
+
+        // lists: element i of every row's list is only ever touched by lane i of the owning warp
+        if (lane < kk_pad) {
+            for (int r = 0; r < 32; ++r) lists[(quad * 32 + r) * kk_pad + lane] = 0ull;
+        }
+        float thr = valid ? -CUDART_INF_F : CUDART_INF_F;
+
+        auto load_bias = [&](int t) -> float {
+            const int r = t * kTileRows + ep_tid;
+            return (r < p.n_local) ? __ldg(p.bias + r) : -CUDART_INF_F;   // -inf masks rows past the shard end
+        };
+        float next_bias = my_tiles > 0 ? load_bias(tile_begin) : 0.f;
+
+        for (int lt = 0; lt < my_tiles; ++lt) {
+            const int t = tile_begin + lt;
+            const int buf = lt & (kAccBufs - 1);
+            const uint32_t bph = (lt / kAccBufs) & 1u;
+            float* bias_tile = bias_s + buf * kTileRows;
+            bias_tile[ep_tid] = next_bias;
+            ptx::named_bar_sync(1, 128);
+            if (lt + 1 < my_tiles) next_bias = load_bias(t + 1);
+
+            ptx::mbar_wait(bar_tfull(buf), bph, p.err, kErrTmemFull);
+            ptx::tc_fence_after();
+
+            if (warp_has_work) {
+                const uint32_t row_base = static_cast<uint32_t>(t) * kTileRows;
+#pragma unroll 1
+                for (int c0 = 0; c0 < kTileRows; c0 += 32) {
+                    uint32_t v[32];
+                    ptx::tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
+                                                buf * kTileRows + c0, v);
+                    ptx::tmem_wait_ld();
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        float s[8];
+                        const float4 b0 = *reinterpret_cast<const float4*>(bias_tile + c0 + g * 8);
+                        const float4 b1 = *reinterpret_cast<const float4*>(bias_tile + c0 + g * 8 + 4);
+                        s[0] = __uint_as_float(v[g * 8 + 0]) + b0.x;
+                        s[1] = __uint_as_float(v[g * 8 + 1]) + b0.y;
+                        s[2] = __uint_as_float(v[g * 8 + 2]) + b0.z;
+                        s[3] = __uint_as_float(v[g * 8 + 3]) + b0.w;
+                        s[4] = __uint_as_float(v[g * 8 + 4]) + b1.x;
+                        s[5] = __uint_as_float(v[g * 8 + 5]) + b1.y;
+                        s[6] = __uint_as_float(v[g * 8 + 6]) + b1.z;
+                        s[7] = __uint_as_float(v[g * 8 + 7]) + b1.w;
+                        if constexpr (kDump) {
+                            if (valid) {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    const uint32_t r = row_base + c0 + g * 8 + i;
+                                    if (r < static_cast<uint32_t>(p.n_local))
+                                        p.dump[static_cast<size_t>(q0 + row) * p.n_local + r] = s[i];
+                                }
+                            }
+                        }
+                        const float m = fmaxf(fmaxf(fmaxf(s[0], s[1]), fmaxf(s[2], s[3])),
+                                              fmaxf(fmaxf(s[4], s[5]), fmaxf(s[6], s[7])));
+                        if (__any_sync(kFullMask, m > thr)) {
+                            // rare path: some query in this warp has a new top-k member among these 8 rows
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                unsigned pending = __ballot_sync(kFullMask, s[i] > thr);
+                                while (pending) {
+                                    const int src = __ffs(pending) - 1;
+                                    pending &= pending - 1;
+                                    const float cs = __shfl_sync(kFullMask, s[i], src);
+                                    const uint64_t key = make_key(cs, p.idx_base + row_base + c0 + g * 8 + i);
+                                    uint64_t* L = lists + (quad * 32 + src) * kk_pad;
+                                    uint64_t e = lane < kk ? L[lane] : 0ull;
+                                    e = warp_list_insert(e, key, lane);
+                                    if (lane < kk) L[lane] = e;
+                                    const uint32_t kth = __shfl_sync(kFullMask, static_cast<uint32_t>(e >> 32), kk - 1);
+                                    if (lane == src)
+                                        thr = kth == 0u ? -CUDART_INF_F : __uint_as_float(ordered_to_f32(kth));
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(bar_tempty(buf));
+        }
+
+        // partial result of this (split, q-tile): part_keys[split][q0 + r][0..kk)
+        if (warp_has_work && lane < kk) {
+            for (int r = 0; r < 32; ++r) {
+                const int qrow = quad * 32 + r;
+                if (qrow < q_valid)
+                    p.part_keys[(static_cast<size_t>(split) * p.b_total + q0 + qrow) * kk + lane] =
+                        lists[qrow * kk_pad + lane];
+            }
+        }
+    }
+
+    // ---- teardown
+    __syncwarp();
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+}  // namespace mpr
