@@ -63,31 +63,36 @@ static int make_plan(mpr_context* h, int b, int64_t n_local, int d, int kk, Scan
     if (kk < 1 || kk > MPR_MAX_KK) return fail(h, MPR_EINVAL, "k + skip must be in [1, %d] (got %d)", MPR_MAX_KK, kk);
 
     pl->n_chunks = d / kChunkK;
-    int q_tile_max = 128;
-    while (q_tile_max > 8 && static_cast<long long>(q_tile_max) * d * 2 > 131072) q_tile_max >>= 1;
-    if (b <= q_tile_max) {
-        pl->q_tile = b;
-        pl->n_qtiles = 1;
-        pl->q_box_rows = pow2_ceil(b) < 8 ? 8 : pow2_ceil(b);
-    } else {
-        pl->q_tile = q_tile_max;
-        pl->n_qtiles = (b + q_tile_max - 1) / q_tile_max;
-        pl->q_box_rows = q_tile_max;
-    }
     pl->kk_pad = pow2_ceil(kk);
     pl->n_tiles = static_cast<int>((n_local + kTileRows - 1) / kTileRows);
+    int q_tile_max = 128;
+    while (q_tile_max > 8 && static_cast<long long>(q_tile_max) * d * 2 > 131072) q_tile_max >>= 1;
+    int stages = 0;
+    for (;;) {
+        if (b <= q_tile_max) {
+            pl->q_tile = b;
+            pl->n_qtiles = 1;
+            pl->q_box_rows = pow2_ceil(b) < 8 ? 8 : pow2_ceil(b);
+        } else {
+            pl->q_tile = q_tile_max;
+            pl->n_qtiles = (b + q_tile_max - 1) / q_tile_max;
+            pl->q_box_rows = q_tile_max;
+        }
+        const ScanSmemLayout fixed = scan_smem_layout(pl->n_chunks, pl->q_box_rows, pl->kk_pad, 0);
+        const int avail = kMaxSmem - 1024 - static_cast<int>(fixed.total);
+        stages = avail / kStageBytes;
+        // the resident q-tile competes with the bank ring for shared memory: keep at least 4 stages (64 KiB) in flight
+        if (stages >= 4 || q_tile_max <= 32 || pl->q_box_rows < q_tile_max) break;
+        q_tile_max >>= 1;
+    }
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (stages < 2) return fail(h, MPR_EINVAL, "shape does not fit shared memory (d=%d, kk=%d)", d, kk);
+    pl->n_stages = stages;
     // items = n_splits * n_qtiles should be a whole number of waves over the SMs
     const int g = std::gcd(h->num_sms, pl->n_qtiles);
     pl->n_splits = h->num_sms / g;
     if (pl->n_splits > pl->n_tiles) pl->n_splits = pl->n_tiles;
     if (pl->n_splits < 1) pl->n_splits = 1;
-
-    const ScanSmemLayout fixed = scan_smem_layout(pl->n_chunks, pl->q_box_rows, pl->kk_pad, 0);
-    const int avail = kMaxSmem - 1024 - static_cast<int>(fixed.total);
-    int stages = avail / kStageBytes;
-    if (stages > kMaxStages) stages = kMaxStages;
-    if (stages < 2) return fail(h, MPR_EINVAL, "shape does not fit shared memory (d=%d, kk=%d)", d, kk);
-    pl->n_stages = stages;
     pl->smem_bytes = scan_smem_layout(pl->n_chunks, pl->q_box_rows, pl->kk_pad, stages).total + 1024u;
     return MPR_OK;
 }

@@ -8,7 +8,7 @@
 // Orientation: queries are the MMA M dimension (one TMEM lane per query), bank rows the N dimension
 // (one TMEM column per row).  Each epilogue thread therefore owns ONE query and walks its lane's columns in
 // ascending row order: the common case per score is one FADD + a share of a max and a vote; only scores that
-// beat the query's current k-th best take the (warp-cooperative) insert path.
+// beat the query's current k-th best are appended to a thread-private pending buffer and folded in later.
 //
 // Work decomposition: item = (bank split s, q-tile t); one CTA per item, blockIdx.x = s * n_qtiles + t, so the
 // CTAs resident at the same time share a bank range and all but the first read of it hit L2.  The q-tile
@@ -37,6 +37,7 @@ constexpr int kScanThreads = 192;
 constexpr int kMaxStages = 12;
 constexpr int kMaxSmem = 232448;              // 227 KiB opt-in limit per CTA on sm_100
 constexpr int kMaxKK = 32;
+constexpr int kCandCap = 16;                  // per-query candidate buffer (flushed when more than 8 are pending)
 
 struct ScanParams {
     int b_total;       // queries in the batch
@@ -62,12 +63,16 @@ struct ScanSmemLayout {
     uint32_t q_off, stage_off, list_off, bias_off, bar_off, total;
 };
 
+// Per-query shared-memory row: [kk_pad sorted keys | kCandCap pending candidates | 1 pad]; the odd stride (in
+// 8-byte words) keeps the 32 lanes of a warp, each walking its own row, on distinct banks.
+__host__ __device__ inline uint32_t scan_row_stride(int kk_pad) { return static_cast<uint32_t>(kk_pad) + kCandCap + 1u; }
+
 __host__ __device__ inline ScanSmemLayout scan_smem_layout(int n_chunks, int q_box_rows, int kk_pad, int n_stages) {
     ScanSmemLayout l;
     l.q_off = 0;
     l.stage_off = static_cast<uint32_t>(n_chunks) * q_box_rows * 128u;          // multiple of 1024
     l.list_off = l.stage_off + static_cast<uint32_t>(n_stages) * kStageBytes;
-    l.bias_off = l.list_off + static_cast<uint32_t>(kUmmaM) * kk_pad * 8u;
+    l.bias_off = l.list_off + static_cast<uint32_t>(kUmmaM) * scan_row_stride(kk_pad) * 8u;
     l.bar_off = l.bias_off + kAccBufs * kTileRows * 4u;
     l.total = l.bar_off + (1 + 2 * kMaxStages + 2 * kAccBufs) * 8u + 16u;
     return l;
@@ -190,6 +195,10 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         }
     } else {
         // =========================== epilogue: streaming top-k ===========================
+        // The 32 lanes of a warp are 32 independent queries, so everything here is thread-private: a lane keeps its
+        // admission threshold (score of its current kk-th best) in a register, appends the rare scores that beat it
+        // to its own pending buffer in shared memory, and — when some lane's buffer runs full — every lane folds
+        // its own pending candidates into its own sorted list.  No cross-lane traffic except one vote per 8 scores.
         const int quad = warp & 3;                     // TMEM lane quadrant this warp may read
         const int row = quad * 32 + lane;              // query slot (TMEM lane) owned by this thread
         const bool valid = row < q_valid;
@@ -197,12 +206,31 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         const int ep_tid = (warp - 2) * 32 + lane;     // 0..127, used to stage the bias tile
         const int kk = p.kk;
         const int kk_pad = p.kk_pad;
-
-        // lists: element i of every row's list is only ever touched by lane i of the owning warp
-        if (lane < kk_pad) {
-            for (int r = 0; r < 32; ++r) lists[(quad * 32 + r) * kk_pad + lane] = 0ull;
-        }
+        uint64_t* my_list = lists + static_cast<size_t>(row) * scan_row_stride(kk_pad);   // [0, kk) sorted keys
+        uint2* my_pend = reinterpret_cast<uint2*>(my_list + kk_pad);                      // (score bits, row)
+        for (int i = 0; i < kk; ++i) my_list[i] = 0ull;
         float thr = valid ? -CUDART_INF_F : CUDART_INF_F;
+        int n_pend = 0;
+
+        auto flush = [&]() {
+            for (int c = 0; c < n_pend; ++c) {
+                const uint2 cand = my_pend[c];
+                const uint64_t key = make_key(__uint_as_float(cand.x), cand.y);
+                if (key > my_list[kk - 1]) {
+                    int j = kk - 1;
+                    while (j > 0) {
+                        const uint64_t above = my_list[j - 1];
+                        if (above >= key) break;
+                        my_list[j] = above;
+                        --j;
+                    }
+                    my_list[j] = key;
+                }
+            }
+            n_pend = 0;
+            const uint64_t kth = my_list[kk - 1];
+            if (valid) thr = kth == 0ull ? -CUDART_INF_F : key_score(kth);
+        };
 
         auto load_bias = [&](int t) -> float {
             const int r = t * kTileRows + ep_tid;
@@ -256,24 +284,17 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                         const float m = fmaxf(fmaxf(fmaxf(s[0], s[1]), fmaxf(s[2], s[3])),
                                               fmaxf(fmaxf(s[4], s[5]), fmaxf(s[6], s[7])));
                         if (__any_sync(kFullMask, m > thr)) {
-                            // rare path: some query in this warp has a new top-k member among these 8 rows
+                            // Rows arrive in ascending order, so a later row can only displace the kk-th best with a
+                            // STRICTLY higher score: `>` is the exact admission test for (score desc, row asc).
+                            const uint32_t gidx = p.idx_base + row_base + c0 + g * 8;
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
-                                unsigned pending = __ballot_sync(kFullMask, s[i] > thr);
-                                while (pending) {
-                                    const int src = __ffs(pending) - 1;
-                                    pending &= pending - 1;
-                                    const float cs = __shfl_sync(kFullMask, s[i], src);
-                                    const uint64_t key = make_key(cs, p.idx_base + row_base + c0 + g * 8 + i);
-                                    uint64_t* L = lists + (quad * 32 + src) * kk_pad;
-                                    uint64_t e = lane < kk ? L[lane] : 0ull;
-                                    e = warp_list_insert(e, key, lane);
-                                    if (lane < kk) L[lane] = e;
-                                    const uint32_t kth = __shfl_sync(kFullMask, static_cast<uint32_t>(e >> 32), kk - 1);
-                                    if (lane == src)
-                                        thr = kth == 0u ? -CUDART_INF_F : __uint_as_float(ordered_to_f32(kth));
+                                if (s[i] > thr) {
+                                    my_pend[n_pend] = make_uint2(__float_as_uint(s[i]), gidx + i);
+                                    ++n_pend;
                                 }
                             }
+                            if (__any_sync(kFullMask, n_pend > kCandCap - 8)) flush();
                         }
                     }
                 }
@@ -283,13 +304,12 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             if (lane == 0) ptx::mbar_arrive(bar_tempty(buf));
         }
 
-        // partial result of this (split, q-tile): part_keys[split][q0 + r][0..kk)
-        if (warp_has_work && lane < kk) {
-            for (int r = 0; r < 32; ++r) {
-                const int qrow = quad * 32 + r;
-                if (qrow < q_valid)
-                    p.part_keys[(static_cast<size_t>(split) * p.b_total + q0 + qrow) * kk + lane] =
-                        lists[qrow * kk_pad + lane];
+        // partial result of this (split, q-tile): part_keys[split][q0 + row][0..kk)
+        if (warp_has_work) {
+            flush();
+            if (valid) {
+                uint64_t* dst = p.part_keys + (static_cast<size_t>(split) * p.b_total + q0 + row) * kk;
+                for (int i = 0; i < kk; ++i) dst[i] = my_list[i];
             }
         }
     }

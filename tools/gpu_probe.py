@@ -72,20 +72,28 @@ for (b, n, d, kk) in [(16, 3072, 1024, 1), (16, 14336, 1024, 2), (128, 100000, 5
     if code:
         print("device error code", code, flush=True)
 # quick timing
-b, n, d, kk = 128, 1250000, 512, 5
-q = (torch.randn(b, d, device=dev) * 0.3).to(torch.bfloat16)
-bank = (torch.randn(n, d, device=dev) * 0.3).to(torch.bfloat16)
-bias = -0.5 * (bank.float() ** 2).sum(1)
-ws = torch.empty(K.search_workspace_bytes(b, n, d, kk), dtype=torch.uint8, device=dev)
-for _ in range(3):
-    K.search_topk(q, bank, bias, kk, workspace=ws)
-torch.cuda.synchronize()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
-for _ in range(20):
-    K.search_topk(q, bank, bias, kk, workspace=ws)
-e1.record()
-torch.cuda.synchronize()
-ms = e0.elapsed_time(e1) / 20
-print(f"timing b={b} n={n} d={d} kk={kk}: {ms*1e3:.1f} us/scan  {n*d*2/ms/1e6:.1f} GB/s  plan={K.search_plan(b,n,d,kk)}", flush=True)
+def timing(b, n, d, kk, iters=20):
+    q = (torch.randn(b, d, device=dev) * 0.3).to(torch.bfloat16)
+    bank = (torch.randn(n, d, device=dev) * 0.3).to(torch.bfloat16)
+    bias = -0.5 * (bank.float() ** 2).sum(1)
+    ws = torch.empty(K.search_workspace_bytes(b, n, d, kk), dtype=torch.uint8, device=dev)
+    ok, os_, oi = K.search_topk(q, bank, bias, kk, workspace=ws)
+    for _ in range(3):
+        K.search_topk(q, bank, bias, kk, workspace=ws, out_keys=ok, out_score=os_, out_idx=oi)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        K.search_topk(q, bank, bias, kk, workspace=ws, out_keys=ok, out_score=os_, out_idx=oi)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    pl = K.search_plan(b, n, d, kk)
+    print(f"timing b={b} n={n} d={d} kk={kk}: {ms*1e3:.1f} us/scan  {n*d*2/ms/1e6:.1f} GB/s  "
+          f"{2*b*n*d/ms/1e9:.1f} TFLOP/s  {b/ms*1e3:.0f} q/s plan={pl}", flush=True)
+
+for (b, n, d, kk) in [(1, 1250000, 512, 5), (16, 1250000, 512, 5), (128, 1250000, 512, 5), (128, 1250000, 512, 1),
+                      (128, 1250000, 512, 32), (64, 1250000, 512, 32), (16, 1000000, 1024, 5), (64, 1000000, 1024, 5),
+                      (256, 1250000, 512, 5), (1024, 1048576, 512, 5), (4096, 1048576, 512, 5)]:
+    timing(b, n, d, kk, iters=10 if b > 256 else 20)
 print("probe done in", time.time() - t0, "s")
