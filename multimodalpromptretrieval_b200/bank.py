@@ -1,0 +1,307 @@
+"""``RetrievalBank`` — host mirror of the retrieval half of the reference's ``VQADataset``.
+
+Same method names, arguments, return shapes and attributes as
+``create_retrieval_dataset`` (/root/reference/dataset/VQAFeatureDataset.py:118-185) and
+``retrieve_closest_qa_pairs`` (:187-246), so ``main.py`` can pass ``bank.retrieve_closest_qa_pairs`` as the model's
+``retrieval_function`` (/root/reference/main.py:123, architectures/T5VisionModel.py:143-147) unchanged.  All of the
+arithmetic — row cast/normalise, scoring, top-k, merge, vote, token gather — runs in ``libmpr_b200.so``; CLIP stays
+stock PyTorch and is reached through the same ``clip_model.encode_image / encode_text`` calls the reference makes.
+
+Differences from the reference that a caller can observe (all documented in DESIGN.md):
+  * the bank is stored bf16 (``retrieval_embeddings`` is this rank's bf16 shard) — scores agree to 1e-3;
+  * exact ties resolve to the lower row index (the reference's unstable argsort leaves them undefined);
+  * ``use_additional_data`` works (the reference crashes at :181) and extends the info dict per key.
+"""
+from __future__ import annotations
+
+import os
+import pickle
+import weakref
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import kernels as K
+from .prompt import PromptTables, bucket_lut, prompt_string
+from .sharding import CandidateExchange, shard_bounds
+
+_INFO_KEYS = ("question_type", "question_id", "question")
+
+
+class RetrievalBank:
+    def __init__(self, clip_model=None, clip_tokenize=None, tokenizer=None, device=None, normalise: bool = False,
+                 process_group=None, shard: bool = True, max_source_length: int = 512, name: str = "VQADataset",
+                 cache_root: str = "cache", additional_root: str = os.path.join("synthetic_data", "cache",
+                                                                               "ROCOFeatureDataset"),
+                 memoise: bool = True):
+        if not torch.cuda.is_available():
+            raise RuntimeError("RetrievalBank needs a B200 (sm_100a) GPU; there is no CPU fallback path")
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.clip_model = clip_model
+        self.clip_tokenize = clip_tokenize
+        self.tokenizer = tokenizer
+        self.normalise = bool(normalise)
+        self.max_source_length = int(max_source_length)
+        self.name = name
+        self.cache_root = cache_root
+        self.additional_root = additional_root
+        self.memoise = memoise
+        self.exchange = CandidateExchange(process_group if shard else None)
+        if not shard:
+            self.exchange.rank, self.exchange.world_size = 0, 1
+        # state the reference keeps on the dataset object (VQAFeatureDataset.py:119-120,128-134,159-161)
+        self.is_training_phase = True
+        self.retrieval_k = 15
+        self.retrieval_embeddings: Optional[torch.Tensor] = None     # bf16 [n_local, D] (this rank's rows)
+        self.retrieval_answers: List[str] = []
+        self.retrieval_question_info: Dict[str, List[str]] = {}
+        # device-side tables
+        self.bias: Optional[torch.Tensor] = None                      # fp32 [n_local] = -0.5*|row|^2
+        self.answer_id: Optional[torch.Tensor] = None                 # int32 [N] interned answers, replicated
+        self.answer_strings: List[str] = []
+        self.n_total = 0
+        self.row_begin = 0
+        self._tables: Optional[PromptTables] = None
+        self._lut_cache: Dict[int, torch.Tensor] = {}
+        self._workspace: Optional[torch.Tensor] = None
+        self._memo = None
+        K.handle(self.device.index)   # fail loudly now if the library / device is unusable
+
+    # ------------------------------------------------------------------------------------------ bank build
+    def create_retrieval_dataset(self, data_loader, prefix, is_training_phase: bool = True, retrieval_k: int = 15,
+                                 use_additional_data: bool = False) -> None:
+        """Same contract as VQAFeatureDataset.py:118-185 (``prefix`` is accepted and unused, as in the reference)."""
+        self.is_training_phase = is_training_phase
+        self.retrieval_k = retrieval_k
+        cache_dir = os.path.join(self.cache_root, self.name)
+        embedding_path = os.path.join(cache_dir, "embedding.pt")
+        question_info_path = os.path.join(cache_dir, "answer_types.pkl")
+        answer_path = os.path.join(cache_dir, "answers.pkl")
+
+        parts: List[Tuple[torch.Tensor, Optional[torch.Tensor]]] = []
+        if os.path.exists(embedding_path) and os.path.exists(answer_path):
+            emb = torch.load(embedding_path, map_location="cpu")
+            print(f"Loaded cached qa lookup embeddings from {embedding_path} ...")
+            with open(answer_path, "rb") as f:
+                answers = pickle.load(f)
+                print(f"Loaded cached qa lookup answers from {answer_path} ...")
+            with open(question_info_path, "rb") as f:
+                info = pickle.load(f)
+                print(f"Loaded cached qa lookup answer types from {question_info_path} ...")
+            parts.append((emb, None))
+        else:
+            os.makedirs(cache_dir, exist_ok=True)
+            print(f"Creating qa pairs in {cache_dir} ...")
+            answers, info = [], {k: [] for k in _INFO_KEYS}
+            host_rows = []
+            with torch.no_grad():
+                for batch in data_loader:
+                    img, txt = self._encode(batch)
+                    parts.append((img, txt))
+                    host_rows.append(torch.cat([img, txt], 1).float().cpu())
+                    answers.extend(batch["answer"])
+                    info["question_type"].extend(batch["question_type"])
+                    info["question_id"].extend(batch["question_id"])
+                    info["question"].extend(batch["question"])
+            if self.exchange.rank == 0:   # reference-format cache (fp32 [N, 1024] + two pickles), :163-167
+                torch.save(torch.cat(host_rows, 0) if host_rows else torch.zeros(0, 0), embedding_path)
+                with open(answer_path, "wb") as f:
+                    pickle.dump(answers, f)
+                with open(question_info_path, "wb") as f:
+                    pickle.dump(info, f)
+
+        if use_additional_data:   # :169-181, with the dict.extend bug at :181 replaced by a per-key extend
+            roco_feats = torch.load(os.path.join(self.additional_root, "embedding.pt"), map_location="cpu")
+            with open(os.path.join(self.additional_root, "answers.pkl"), "rb") as f:
+                roco_ans = pickle.load(f)
+            with open(os.path.join(self.additional_root, "answer_types.pkl"), "rb") as f:
+                roco_info = pickle.load(f)
+            parts.append((roco_feats, None))
+            answers = list(answers) + list(roco_ans)
+            info = {k: list(v) + list(roco_info.get(k, [])) for k, v in info.items()}
+
+        self.install_bank(parts, answers, info)
+        print(f"Retrieval features shape: {torch.Size([self.n_total, self.dim])}")
+        print(f"Number of answers: {len(self.retrieval_answers)}")
+
+    def install_bank(self, parts: Iterable[Tuple[torch.Tensor, Optional[torch.Tensor]]], answers: Sequence[str],
+                     info: Dict[str, Sequence[str]], is_training_phase: Optional[bool] = None,
+                     retrieval_k: Optional[int] = None) -> None:
+        """Lays the bank out in HBM.  ``parts`` is a sequence of row blocks in global row order, each either
+        ``(combined [n, D], None)`` or ``(image_half [n, d0], text_half [n, d1])``, fp32/fp16/bf16, on any device.
+        Kernel 1 casts (and optionally normalises) every block straight into this rank's bf16 shard."""
+        if is_training_phase is not None:
+            self.is_training_phase = is_training_phase
+        if retrieval_k is not None:
+            self.retrieval_k = retrieval_k
+        parts = list(parts)
+        n_total = sum(int(p[0].shape[0]) for p in parts)
+        if n_total == 0:
+            raise ValueError("empty retrieval bank")
+        dim = int(parts[0][0].shape[1] + (parts[0][1].shape[1] if parts[0][1] is not None else 0))
+        if len(answers) != n_total:
+            raise ValueError(f"{len(answers)} answers for {n_total} bank rows")
+        begin, end = shard_bounds(n_total, self.exchange.rank, self.exchange.world_size)
+        n_local = end - begin
+        bank = torch.empty((max(n_local, 1), dim), dtype=torch.bfloat16, device=self.device)[:n_local]
+        bias = torch.empty((max(n_local, 1),), dtype=torch.float32, device=self.device)[:n_local]
+        row = 0
+        chunk_rows = max(1, (256 << 20) // (dim * 4))       # stage host blocks through <= 256 MiB device buffers
+        for a, b in parts:
+            n = int(a.shape[0])
+            lo, hi = max(begin, row), min(end, row + n)
+            for c0 in range(lo, hi, chunk_rows):
+                c1 = min(hi, c0 + chunk_rows)
+                sa = a[c0 - row:c1 - row].to(self.device, non_blocking=True).contiguous()
+                sb = None if b is None else b[c0 - row:c1 - row].to(self.device, non_blocking=True).contiguous()
+                if sa.dtype not in (torch.float32, torch.float16, torch.bfloat16):
+                    sa = sa.float()
+                    sb = None if sb is None else sb.float()
+                K.bank_build(sa, sb, normalise=self.normalise, out=bank[c0 - begin:c1 - begin],
+                             bias=bias[c0 - begin:c1 - begin])
+            row += n
+        self.retrieval_embeddings = bank
+        self.bias = bias
+        self.n_total, self.dim, self.row_begin = n_total, dim, begin
+        self.retrieval_answers = list(answers)
+        self.retrieval_question_info = {k: list(v) for k, v in info.items()}
+        # intern the answers: bank row -> answer id, replicated on every rank (4 B/row)
+        table: Dict[str, int] = {}
+        ids = np.empty(n_total, dtype=np.int32)
+        for i, a in enumerate(self.retrieval_answers):
+            ids[i] = table.setdefault(a, len(table))
+        self.answer_strings = list(table.keys())
+        self.answer_id = torch.from_numpy(ids).to(self.device)
+        self._tables = None
+        self._memo = None
+
+    # ------------------------------------------------------------------------------------------ query path
+    def _encode(self, batch) -> Tuple[torch.Tensor, torch.Tensor]:
+        """The two CLIP calls of VQAFeatureDataset.py:146-147 / :189-190 (stock PyTorch, out of scope)."""
+        img = self.clip_model.encode_image(batch["image"].to(self.device))
+        tokens = self.clip_tokenize(batch["question"]) if self.clip_tokenize is not None else batch["question"]
+        if isinstance(tokens, torch.Tensor):
+            tokens = tokens.to(self.device)
+        txt = self.clip_model.encode_text(tokens)
+        return img.detach().contiguous(), txt.detach().contiguous()
+
+    def search_embeddings(self, image_half: torch.Tensor, text_half: Optional[torch.Tensor] = None, kk: Optional[int] = None
+                          ) -> Dict[str, torch.Tensor]:
+        """Query halves (device tensors) -> global top-(k+skip): ``score`` fp32 / ``idx`` int32 ``[B, kk]`` and
+        ``q_sqnorm`` fp32 ``[B]``.  Kernel 1 (queries) -> kernel 2 (+4) -> [all-gather -> kernel 4]."""
+        if kk is None:
+            kk = self.retrieval_k + (1 if self.is_training_phase else 0)
+        q, qbias = K.bank_build(image_half, text_half, normalise=self.normalise)
+        b = q.shape[0]
+        n_local = self.retrieval_embeddings.shape[0]
+        if n_local > 0:
+            need = K.search_workspace_bytes(b, n_local, self.dim, kk, self.device.index)
+            if self._workspace is None or self._workspace.numel() < need:
+                self._workspace = torch.empty((max(need, 16),), dtype=torch.uint8, device=self.device)
+            keys, score, idx = K.search_topk(q, self.retrieval_embeddings, self.bias, kk, idx_base=self.row_begin,
+                                             workspace=self._workspace)
+        else:
+            keys = torch.zeros((b, kk), dtype=torch.int64, device=self.device)
+            score = torch.full((b, kk), float("-inf"), device=self.device)
+            idx = torch.full((b, kk), -1, dtype=torch.int32, device=self.device)
+        if self.exchange.world_size > 1:
+            keys, score, idx = K.merge_topk(self.exchange.gather(keys))
+        return {"keys": keys, "score": score, "idx": idx, "q_sqnorm": qbias * -2.0}
+
+    def _lut(self, k: int) -> torch.Tensor:
+        t = self._lut_cache.get(k)
+        if t is None:
+            t = torch.from_numpy(bucket_lut(k)).to(self.device)
+            self._lut_cache[k] = t
+        return t
+
+    def _prompt_tables(self) -> PromptTables:
+        if self._tables is None:
+            if self.tokenizer is None:
+                raise RuntimeError("a T5 tokenizer is required for token-id output")
+            self._tables = PromptTables(self.tokenizer, self.answer_strings, self.device)
+        return self._tables
+
+    def _retrieve(self, batch) -> dict:
+        """One search per batch object; the reference re-embeds and re-searches the same batch up to 5 times
+        (main.py:178-179, 263-270) — results are memoised on the identity of ``batch["image"]``."""
+        img_t = batch["image"]
+        if self.memoise and self._memo is not None:
+            ref, questions, out = self._memo
+            if ref() is img_t and questions == list(batch["question"]):
+                return out
+        skip = 1 if self.is_training_phase else 0
+        k = self.retrieval_k
+        with torch.no_grad():
+            img, txt = self._encode(batch)
+        res = self.search_embeddings(img, txt, kk=k + skip)
+        # vote on the device (kernel 3 without tokens needs no tokenizer: empty segment tables)
+        out = {"skip": skip, "k": k, "device": res}
+        idx_h = res["idx"].cpu().numpy()
+        score_h = res["score"].cpu().numpy()
+        qsq_h = res["q_sqnorm"].cpu().numpy()
+        out["idx"] = idx_h
+        out["score"] = score_h
+        out["q_sqnorm"] = qsq_h
+        if self.memoise:
+            try:
+                self._memo = (weakref.ref(img_t), list(batch["question"]), out)
+            except TypeError:
+                self._memo = None
+        return out
+
+    def retrieve_closest_qa_pairs(self, batch, return_ans: bool = False, return_info=None, return_dists: bool = False,
+                                  use_quantifier: bool = True):
+        """Same contract as VQAFeatureDataset.py:187-246 (precedence return_ans > return_info > return_dists)."""
+        r = self._retrieve(batch)
+        skip, k = r["skip"], r["k"]
+        top = r["idx"][:, skip:skip + k]
+        answers = [[self.retrieval_answers[int(x)] for x in row if x >= 0] for row in top]            # :199
+        if return_ans:
+            return answers
+        if return_info:                                                                               # :202-210
+            out = []
+            for row in top:
+                info: List[str] = []
+                for idx in row:
+                    if idx >= 0:
+                        info.extend(self.retrieval_question_info[entry][int(idx)] for entry in return_info)
+                out.append(info)
+            return out
+        if return_dists:
+            # :243 sorts the whole matrix again and takes ranks 0..k-1 WITHOUT the training skip; reproduced here.
+            d2 = r["q_sqnorm"][:, None] - 2.0 * r["score"][:, 0:k]
+            dists = np.sqrt(np.maximum(d2, 0.0)).astype(np.float32)
+            return list(zip(answers, dists))
+        vote = self._vote(r)
+        maj, bkt = vote["majority_answer"], vote["bucket"]
+        return [prompt_string(int(bkt[i]), self.answer_strings[int(maj[i])], use_quantifier) for i in range(len(maj))]
+
+    def _vote(self, r: dict) -> dict:
+        if "vote" not in r:
+            res = r["device"]
+            dummy = torch.zeros(16, dtype=torch.int32, device=self.device)
+            b = res["idx"].shape[0]
+            out = K.prompt_gather(res["idx"], r["skip"], self.answer_id, self._lut(r["k"]), dummy,
+                                  torch.zeros(b + 1, dtype=torch.int32, device=self.device), dummy,
+                                  torch.zeros(9 + len(self.answer_strings), dtype=torch.int32, device=self.device),
+                                  True, 0, 1, 2, 1)
+            r["vote"] = {k_: out[k_].cpu().numpy() for k_ in ("majority_answer", "majority_count", "bucket", "answer_ids")}
+        return r["vote"]
+
+    def retrieve_prompt_ids(self, batch, use_quantifier: bool = True, pad_to: str = "longest"):
+        """Additive fast path for ``prepare_input`` (architectures/T5VisionModel.py:143-167): returns the
+        ``input_ids`` / ``attention_mask`` the reference's tokenizer call would produce for
+        ``task_prefix + question + retrieved_info`` — assembled on the device by kernel 3, no strings involved."""
+        r = self._retrieve(batch)
+        tables = self._prompt_tables()
+        pre_ids, pre_off, longest = tables.prefixes(batch["task"], batch["question"], use_quantifier)
+        stride = min(self.max_source_length, longest + tables.tail_bound(use_quantifier))
+        out = K.prompt_gather(r["device"]["idx"], r["skip"], self.answer_id, self._lut(r["k"]), pre_ids, pre_off,
+                              tables.seg_ids, tables.seg_off, use_quantifier, tables.pad_id, tables.eos_id,
+                              self.max_source_length, stride)
+        if pad_to == "longest":        # exact shape parity with padding="longest" costs one tiny D2H sync
+            longest_out = int(out["length"].max().item())
+            return out["input_ids"][:, :longest_out], out["attention_mask"][:, :longest_out]
+        return out["input_ids"], out["attention_mask"]

@@ -1,0 +1,103 @@
+"""Host side of the prompt-token gather (kernel 3): pre-tokenised segment tables, the quantifier bucket LUT and the
+per-query prefix tokens.
+
+The reference builds one string per query and runs the T5 tokenizer on it
+(/root/reference/architectures/T5VisionModel.py:153-167):
+
+    "Answer the {task} question: " + question + "I believe the answer is {bucket} {answer}"      (quantifier on)
+    "Answer the {task} question: " + question + "The most frequent answer is {answer}"            (quantifier off)
+
+There is no space between the question and the retrieved sentence, so the question's last word fuses with
+"I" / "The" (e.g. ``lung?I``).  Sentencepiece never forms a piece across a whitespace boundary, so the token sequence
+of the whole sentence is the concatenation of
+
+    tokens(prefix + "I" | "The")  ‖  tokens("believe the answer is" | "most frequent answer is")
+                                  ‖  tokens(bucket)  ‖  tokens(answer)  ‖  </s>
+
+Only the first term depends on the query text; it is tokenised on the host (it does not depend on retrieval, so it
+can overlap the bank scan).  Everything else is gathered on the device from tables built once per bank.
+"""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple
+
+import numpy as np
+import torch
+
+BUCKETS = ["very unlikely", "unlikely", "maybe", "likely", "very likely", "certainly"]   # VQAFeatureDataset.py:188
+HEAD_QUANT, TAIL_QUANT = "I", "believe the answer is"                                    # VQAFeatureDataset.py:228
+HEAD_PLAIN, TAIL_PLAIN = "The", "most frequent answer is"                                # VQAFeatureDataset.py:230
+SEG_QUANT, SEG_PLAIN, SEG_BUCKET0, SEG_ANSWER0 = 0, 1, 2, 8                              # csrc/prompt_gather.cuh
+
+
+def bucket_lut(k: int) -> np.ndarray:
+    """lut[n_votes*(k+1) + max_count] = int(max_count / n_votes * 5), evaluated in Python float64 exactly as
+    VQAFeatureDataset.py:223-226 does (e.g. 3/5*5 = 3.0000000000000004 -> 3)."""
+    lut = np.zeros((k + 1, k + 1), dtype=np.uint8)
+    for n in range(1, k + 1):
+        for m in range(1, n + 1):
+            certainty = m / n
+            lut[n, m] = int(certainty * (len(BUCKETS) - 1))
+    return lut.reshape(-1)
+
+
+def prompt_string(bucket: int, answer: str, use_quantifier: bool) -> str:
+    """The sentence retrieve_closest_qa_pairs returns (VQAFeatureDataset.py:228,230)."""
+    if use_quantifier:
+        return f"{HEAD_QUANT} {TAIL_QUANT} {BUCKETS[bucket]} {answer}"
+    return f"{HEAD_PLAIN} {TAIL_PLAIN} {answer}"
+
+
+def segment_strings(answer_strings: Sequence[str]) -> List[str]:
+    """Segment table order expected by kernel 3: two constant tails, six buckets, then the answers."""
+    return [TAIL_QUANT, TAIL_PLAIN] + BUCKETS + list(answer_strings)
+
+
+def prefix_texts(tasks: Sequence[str], questions: Sequence[str], use_quantifier: bool) -> List[str]:
+    """Per-query text tokenised on the host: task prefix + question + the fused first word of the retrieved
+    sentence (T5VisionModel.py:153,158)."""
+    head = HEAD_QUANT if use_quantifier else HEAD_PLAIN
+    return [f"Answer the {t} question: " + q + head for t, q in zip(tasks, questions)]
+
+
+def _csr(rows: Sequence[Sequence[int]]) -> Tuple[np.ndarray, np.ndarray]:
+    off = np.zeros(len(rows) + 1, dtype=np.int32)
+    np.cumsum([len(r) for r in rows], out=off[1:])
+    ids = np.fromiter((t for r in rows for t in r), dtype=np.int32, count=int(off[-1]))
+    return ids, off
+
+
+class PromptTables:
+    """Device-resident CSR of the constant segments, the six buckets and every distinct answer of the bank."""
+
+    def __init__(self, tokenizer, answer_strings: Sequence[str], device: torch.device):
+        self.tokenizer = tokenizer
+        self.pad_id = int(tokenizer.pad_token_id)
+        self.eos_id = int(tokenizer.eos_token_id)
+        segs = segment_strings(answer_strings)
+        enc = tokenizer(segs, add_special_tokens=False)["input_ids"] if segs else []
+        ids, off = _csr(enc)
+        self.seg_lens = np.diff(off)
+        self.max_answer_len = int(self.seg_lens[SEG_ANSWER0:].max()) if len(answer_strings) else 0
+        self.seg_ids = torch.from_numpy(ids if ids.size else np.zeros(1, np.int32)).to(device)
+        self.seg_off = torch.from_numpy(off).to(device)
+        self.device = device
+
+    def tail_bound(self, use_quantifier: bool) -> int:
+        """Upper bound on tokens appended after the prefix (const + bucket + answer + </s>)."""
+        if use_quantifier:
+            return int(self.seg_lens[SEG_QUANT]) + int(self.seg_lens[SEG_BUCKET0:SEG_ANSWER0].max()) + \
+                self.max_answer_len + 1
+        return int(self.seg_lens[SEG_PLAIN]) + self.max_answer_len + 1
+
+    def prefixes(self, tasks: Sequence[str], questions: Sequence[str], use_quantifier: bool
+                 ) -> Tuple[torch.Tensor, torch.Tensor, int]:
+        """tokens("Answer the {task} question: " + question + "I"|"The") per query as a device CSR, plus the
+        longest prefix length."""
+        texts = prefix_texts(tasks, questions, use_quantifier)
+        enc = self.tokenizer(texts, add_special_tokens=False)["input_ids"]
+        ids, off = _csr(enc)
+        longest = int(np.diff(off).max()) if len(texts) else 0
+        ids_t = torch.from_numpy(ids if ids.size else np.zeros(1, np.int32)).pin_memory().to(self.device, non_blocking=True)
+        off_t = torch.from_numpy(off).pin_memory().to(self.device, non_blocking=True)
+        return ids_t, off_t, longest

@@ -1,0 +1,386 @@
+"""GPU parity tests: every kernel is driven through the C ABI (libmpr_b200.so) and checked against the CPU oracle
+(oracle/retrieval_oracle.py) on identical bf16-rounded inputs, plus the reference-generated golden fixtures.
+
+Parity bar (BASELINE.json north_star): retrieved indices and prompt token ids bit-exact, except where two candidates'
+oracle scores differ by <= 1e-3; scores within 1e-3 absolute.
+"""
+import os
+import pickle
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import retrieval_oracle as O
+from tests.conftest import GOLDEN_CASES
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def K():
+    from multimodalpromptretrieval_b200 import kernels
+    kernels.handle(0)
+    return kernels
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def clip_like(n, d, seed, norm=10.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(n, d, generator=g) * (norm / d ** 0.5)).to(torch.bfloat16)
+
+
+def oracle_topk(q, bank, kk):
+    s = O.scores_f64(q.float(), bank.float())
+    order = torch.argsort(-s, dim=1, stable=True)[:, :kk]
+    return s, order.numpy(), torch.gather(s, 1, order).numpy()
+
+
+# ------------------------------------------------------------------------------------------------ kernel 1
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("d0,d1", [(512, 512), (512, 0), (64, 0), (256, 64)])
+def test_bank_build_cast_and_bias(K, dtype, d0, d1):
+    g = torch.Generator().manual_seed(d0 + d1)
+    n = 1037
+    a = (torch.randn(n, d0, generator=g) * 0.3).to(dtype)
+    b = (torch.randn(n, d1, generator=g) * 0.3).to(dtype) if d1 else None
+    out, bias = K.bank_build(a.to(dev()), None if b is None else b.to(dev()))
+    x = torch.cat([a, b], 1).float() if d1 else a.float()
+    ref = x.to(torch.bfloat16)
+    assert torch.equal(out.cpu(), ref)                                   # cast is bit-exact (RN-even)
+    ref_bias = -0.5 * ref.double().pow(2).sum(1)
+    assert (bias.cpu().double() - ref_bias).abs().max().item() < 1e-4
+
+
+def test_bank_build_normalise(K):
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2000, 1024, generator=g) * 0.3
+    x[7] = 0
+    out, bias = K.bank_build(x.to(dev()), normalise=True)
+    ref = (x / x.norm(dim=1, keepdim=True).clamp_min(1e-30)).to(torch.bfloat16)
+    out_c = out.cpu()
+    assert torch.equal(out_c[7], torch.zeros(1024, dtype=torch.bfloat16))
+    diff_ulps = (out_c.view(torch.int16).int() - ref.view(torch.int16).int()).abs()
+    assert diff_ulps.max().item() <= 1                                   # norm summation order: at most 1 bf16 ulp
+    assert (diff_ulps > 0).float().mean().item() < 1e-3
+    assert (bias.cpu()[:7] + 0.5).abs().max().item() < 2e-3              # |row| = 1 up to bf16 rounding
+
+
+def test_bank_build_rejects_bad_arguments(K):
+    from multimodalpromptretrieval_b200._native import NativeError
+    with pytest.raises(NativeError):
+        K.bank_build(torch.zeros(4, 100, device=dev()))                  # D % 64 != 0
+    with pytest.raises(NativeError):
+        K.bank_build(torch.zeros(4, 4096, device=dev()))                 # D > 2048
+
+
+# ------------------------------------------------------------------------------------------------ kernel 2: scores
+@pytest.mark.parametrize("b,n,d", [(1, 1, 64), (16, 128, 64), (16, 3072, 1024), (5, 300, 1024), (128, 1000, 512),
+                                   (200, 5000, 512), (33, 129, 256), (70, 2000, 1024), (8, 777, 2048)])
+def test_score_matrix_matches_oracle(K, b, n, d):
+    q, bank = clip_like(b, d, 1), clip_like(n, d, 2)
+    qd, bd = q.to(dev()), bank.to(dev())
+    _, bias = K.bank_build(bd)
+    s = K.debug_scores(qd, bd, bias).cpu().double()
+    ref = O.scores_f64(q.float(), bank.float())
+    assert not torch.isnan(s).any()
+    assert (s - ref).abs().max().item() < TOL
+    assert K.handle(0).device_error() == 0
+
+
+# ------------------------------------------------------------------------------------------------ kernel 2+4: top-k
+TOPK_CASES = [
+    # b, n, d, kk
+    (16, 3072, 1024, 1), (16, 3072, 1024, 2), (16, 14336, 1024, 1), (16, 14336, 1024, 6), (1, 5000, 512, 32),
+    (128, 20000, 512, 5), (129, 20000, 512, 5), (300, 30000, 512, 16), (64, 2000, 1024, 15), (65, 2000, 1024, 16),
+    (7, 127, 64, 3), (7, 128, 64, 3), (7, 129, 64, 3), (3, 1, 64, 1), (40, 50000, 256, 31),
+]
+
+
+@pytest.mark.parametrize("b,n,d,kk", TOPK_CASES)
+def test_topk_matches_oracle(K, b, n, d, kk):
+    q, bank = clip_like(b, d, 10 + b), clip_like(n, d, 20 + kk)
+    half = min(b // 2, n)
+    if half:
+        q[:half] = (bank[:half].float() * 1.01).to(torch.bfloat16)        # near-self matches
+    qd, bd = q.to(dev()), bank.to(dev())
+    _, bias = K.bank_build(bd)
+    keys, score, idx = K.search_topk(qd, bd, bias, kk)
+    s_ref, idx_ref, top_ref = oracle_topk(q, bank, kk)
+    kq = min(kk, n)
+    idx_h, score_h = idx.cpu().numpy(), score.cpu().numpy()
+    O.check_index_parity(idx_h[:, :kq].astype(np.int64), s_ref, idx_ref[:, :kq], TOL)
+    assert np.abs(score_h[:, :kq] - top_ref[:, :kq]).max() < TOL
+    assert (idx_h[:, kq:] == -1).all() and np.isneginf(score_h[:, kq:]).all()   # fewer than kk rows exist
+    s_dec, i_dec = O.decode_keys(keys.cpu().numpy().view(np.uint64))
+    assert np.array_equal(i_dec, idx_h) and np.array_equal(s_dec[:, :kq], score_h[:, :kq])
+    assert K.handle(0).device_error() == 0
+
+
+def test_exact_ties_resolve_to_lower_row(K):
+    """VQA_RAD-style exact duplicate rows: identical scores, the lower row must rank first — across
+    tiles, across CTAs (splits) and within a tile."""
+    n, d, kk = 40000, 512, 8
+    bank = clip_like(n, d, 5)
+    dup_of = {130: 3, 131: 3, 20000: 3, 39999: 3, 517: 516, 25000: 9000}
+    for dst, src in dup_of.items():
+        bank[dst] = bank[src]
+    q = torch.cat([bank[[3, 516, 9000]].clone(), clip_like(5, d, 6)])
+    qd, bd = q.to(dev()), bank.to(dev())
+    _, bias = K.bank_build(bd)
+    _, score, idx = K.search_topk(qd, bd, bias, kk)
+    _, idx_ref, _ = oracle_topk(q, bank, kk)
+    idx_h = idx.cpu().numpy()
+    assert idx_h[0, :5].tolist() == [3, 130, 131, 20000, 39999]
+    assert idx_h[1, :2].tolist() == [516, 517] and idx_h[2, :2].tolist() == [9000, 25000]
+    assert np.array_equal(idx_h[:3, :2], idx_ref[:3, :2])
+    sc = score.cpu().numpy()
+    assert (sc[0, :5] == sc[0, 0]).all()                                 # bit-identical scores for identical rows
+
+
+def test_search_rejects_bad_arguments(K):
+    from multimodalpromptretrieval_b200._native import NativeError
+    q, bank = clip_like(4, 128, 1).to(dev()), clip_like(100, 128, 2).to(dev())
+    bias = torch.zeros(100, device=dev())
+    with pytest.raises(NativeError):
+        K.search_topk(q, bank, bias, 33)                                 # k + skip > 32
+    with pytest.raises(NativeError):
+        K.search_topk(q, bank, bias, 0)
+    q96, bank96 = clip_like(4, 96, 1).to(dev()), clip_like(100, 96, 2).to(dev())
+    with pytest.raises(NativeError):
+        K.search_topk(q96, bank96, bias, 1)                              # D % 64 != 0
+
+
+def test_full_size_bank_properties(K):
+    """BASELINE-size shard (1.25 M x 512 bf16 = one GPU's share of the 10 M bank): planted neighbours are found in
+    order, and the result equals a chunked fp32 torch scan under the 1e-3 rule."""
+    n, d, b, kk = 1_250_000, 512, 128, 5
+    g = torch.Generator(device="cuda").manual_seed(88)
+    src = torch.randn(n, d, device=dev(), generator=g) * (10.0 / d ** 0.5)
+    bank, bias = K.bank_build(src)
+    del src
+    rows = torch.randint(0, n, (b,), device=dev(), generator=g)
+    q = bank[rows].clone()                                               # exact copies: the row itself must be rank 0
+    _, score, idx = K.search_topk(q, bank, bias, kk)
+    best = torch.full((b, kk), float("-inf"), device=dev())
+    best_i = torch.zeros((b, kk), dtype=torch.int64, device=dev())
+    for c0 in range(0, n, 250_000):
+        blk = bank[c0:c0 + 250_000].float()
+        s = q.float() @ blk.T + bias[c0:c0 + 250_000][None, :]
+        cs, ci = torch.topk(s, kk, dim=1)
+        allv, alli = torch.cat([best, cs], 1), torch.cat([best_i, ci + c0], 1)
+        best, sel = torch.topk(allv, kk, dim=1)
+        best_i = torch.gather(alli, 1, sel)
+    assert (score - best).abs().max().item() < TOL
+    mism = idx.long() != best_i
+    gap = (score - best).abs()
+    assert (gap[mism] < TOL).all()
+    self_score = -bias[rows]                                             # <b,b> - 0.5|b|^2 = 0.5|b|^2
+    assert (score[:, 0] - self_score).abs().max().item() < TOL
+    assert (idx[:, 0].long() == rows).float().mean().item() > 0.99       # (a random duplicate row would also tie)
+    assert K.handle(0).device_error() == 0
+
+
+# ------------------------------------------------------------------------------------------------ kernel 4: merge
+@pytest.mark.parametrize("n_lists,b,kk", [(1, 5, 3), (2, 16, 6), (8, 128, 5), (148, 33, 32), (37, 300, 1)])
+def test_merge_matches_oracle(K, n_lists, b, kk):
+    rng = np.random.default_rng(n_lists * 100 + kk)
+    score = rng.standard_normal((n_lists, b, kk)).astype(np.float32)
+    score[0, :, : kk // 2] = 0.5                                          # plenty of exact score ties
+    idx = rng.permutation(n_lists * b * kk).reshape(n_lists, b, kk).astype(np.int32)
+    keys = O.keys_from(score, idx)
+    keys = np.sort(keys, axis=2)[:, :, ::-1].copy()                       # every input list sorted descending
+    if n_lists > 1:
+        keys[1, :, kk - 1] = 0                                            # an empty slot
+    out_keys, out_score, out_idx = K.merge_topk(torch.from_numpy(keys.view(np.int64)).to(dev()))
+    ref = O.merge_keys(keys, kk)
+    assert np.array_equal(out_keys.cpu().numpy().view(np.uint64), ref)
+    s_ref, i_ref = O.decode_keys(ref)
+    assert np.array_equal(out_idx.cpu().numpy(), i_ref)
+    got = out_score.cpu().numpy()
+    assert np.array_equal(got[ref != 0], s_ref[ref != 0])
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_search_equals_single_shard(K, world):
+    """Multi-GPU path emulated on one GPU: per-rank shard scans with their idx_base, candidate lists stacked as the
+    all-gather would deliver them, merged by kernel 4 — identical (keys, bit for bit) to the unsharded search."""
+    from multimodalpromptretrieval_b200.sharding import shard_bounds
+    n, d, b, kk = 30011, 512, 48, 6
+    bank = clip_like(n, d, 77)
+    bank[29000] = bank[5]                                                 # duplicate across shards
+    q = torch.cat([bank[:24].clone(), clip_like(24, d, 78)])
+    qd, bd = q.to(dev()), bank.to(dev())
+    _, bias = K.bank_build(bd)
+    full_keys, _, full_idx = K.search_topk(qd, bd, bias, kk)
+    parts = []
+    for r in range(world):
+        b0, b1 = shard_bounds(n, r, world)
+        k_r, _, _ = K.search_topk(qd, bd[b0:b1].contiguous(), bias[b0:b1].contiguous(), kk, idx_base=b0)
+        parts.append(k_r)
+    keys, _, idx = K.merge_topk(torch.stack(parts, 0).contiguous())
+    assert torch.equal(keys, full_keys) and torch.equal(idx, full_idx)
+    assert idx[5, :2].tolist() == [5, 29000]
+
+
+# ------------------------------------------------------------------------------------------------ kernel 3
+def _oracle_prompt_ids(tokenizer, tasks, questions, answers_rows, use_quantifier, max_len):
+    retrieved = [O.prompt_sentence(r, use_quantifier) for r in answers_rows]
+    return O.tokenize(tokenizer, O.input_sentences(tasks, questions, retrieved), max_len)
+
+
+@pytest.mark.parametrize("k,skip,quant,max_len", [(1, 0, True, 512), (1, 1, True, 512), (5, 1, True, 512),
+                                                  (5, 0, False, 512), (15, 0, True, 512), (32, 0, True, 512),
+                                                  (31, 1, False, 512), (5, 0, True, 24)])
+def test_prompt_gather_matches_oracle(K, tokenizer, k, skip, quant, max_len):
+    from multimodalpromptretrieval_b200 import prompt as P
+    from multimodalpromptretrieval_b200 import synthetic as S
+    rng = np.random.default_rng(k * 7 + skip)
+    vocab = S.answer_vocab(12, 88)                                        # few answers -> many vote ties
+    n, b = 500, 37
+    row_answers = [vocab[i] for i in rng.integers(0, len(vocab), n)]
+    table = {}
+    answer_id = np.array([table.setdefault(a, len(table)) for a in row_answers], dtype=np.int32)
+    strings = list(table.keys())
+    idx = np.stack([rng.permutation(n)[: k + skip] for _ in range(b)]).astype(np.int32)
+    questions = [f"{q} #{i}" for i, q in enumerate(S.make_questions(b, 5))]
+    tasks = [S.TASKS[i % len(S.TASKS)] for i in range(b)]
+    tables = P.PromptTables(tokenizer, strings, dev())
+    pre_ids, pre_off, longest = tables.prefixes(tasks, questions, quant)
+    stride = min(max_len, longest + tables.tail_bound(quant))
+    out = K.prompt_gather(torch.from_numpy(idx).to(dev()), skip, torch.from_numpy(answer_id).to(dev()),
+                          torch.from_numpy(P.bucket_lut(k)).to(dev()), pre_ids, pre_off, tables.seg_ids,
+                          tables.seg_off, quant, tables.pad_id, tables.eos_id, max_len, stride)
+    rows = [[row_answers[j] for j in idx[i, skip:]] for i in range(b)]
+    ids_ref, mask_ref = _oracle_prompt_ids(tokenizer, tasks, questions, rows, quant, max_len)
+    longest_out = int(out["length"].max().item())
+    assert longest_out == ids_ref.shape[1]
+    assert torch.equal(out["input_ids"][:, :longest_out].cpu(), ids_ref)
+    assert torch.equal(out["attention_mask"][:, :longest_out].cpu(), mask_ref)
+    for i in range(b):
+        ans, m, nv = O.vote(rows[i])
+        assert strings[int(out["majority_answer"][i])] == ans
+        assert int(out["majority_count"][i]) == m and int(out["bucket"][i]) == O.bucket_index(m, nv)
+    assert np.array_equal(out["answer_ids"].cpu().numpy(), answer_id[idx[:, skip:]])
+
+
+def test_prompt_gather_with_fewer_rows_than_k(K):
+    """k > N: the reference's slice simply returns fewer columns; votes are over the rows that exist."""
+    from multimodalpromptretrieval_b200 import prompt as P
+    idx = torch.tensor([[4, 2, -1, -1], [1, -1, -1, -1]], dtype=torch.int32, device=dev())
+    answer_id = torch.tensor([0, 1, 2, 0, 2], dtype=torch.int32, device=dev())
+    z = torch.zeros(16, dtype=torch.int32, device=dev())
+    out = K.prompt_gather(idx, 0, answer_id, torch.from_numpy(P.bucket_lut(4)).to(dev()), z, z[:3], z, z[:12],
+                          True, 0, 1, 8, 4)
+    assert out["majority_answer"].tolist() == [2, 1] and out["majority_count"].tolist() == [2, 1]
+    assert out["bucket"].tolist() == [5, 5]                               # 2/2 and 1/1 -> "certainly"
+
+
+# ------------------------------------------------------------------------------------------------ host class vs golden
+class _Clip:
+    def encode_image(self, x):
+        return x
+
+    def encode_text(self, x):
+        return x
+
+
+def _bank_from_golden(g, tokenizer, **kw):
+    from multimodalpromptretrieval_b200.bank import RetrievalBank
+    table = {q: e for q, e in zip(g.questions, g.q_txt)}
+    tok = lambda qs: torch.stack([table[q] for q in qs], 0)
+    bank = RetrievalBank(clip_model=_Clip(), clip_tokenize=tok, tokenizer=tokenizer, shard=False, **kw)
+    bank.install_bank([(g.bank_img, g.bank_txt)], g.answers, g.info, is_training_phase=g.training, retrieval_k=g.k)
+    batch = {"image": g.q_img.clone(), "question": g.questions, "task": g.tasks}
+    return bank, batch
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_retrieval_bank_reproduces_reference_golden(name, golden_cases, tokenizer):
+    g = golden_cases[name]
+    bank, batch = _bank_from_golden(g, tokenizer)
+    r = bank._retrieve(batch)
+    s_ref = O.scores_f64(g.queries(), g.bank())
+    skip = 1 if g.training else 0
+    top = r["idx"][:, skip:skip + g.k].astype(np.int64)
+    _, tolerated = O.check_index_parity(top, s_ref, g.z["top_idx"].astype(np.int64), TOL)
+    dists = bank.retrieve_closest_qa_pairs(batch, return_dists=True)
+    assert np.abs(np.stack([d for _, d in dists]) - g.z["return_dists"]).max() < TOL
+    assert all(d.dtype == np.float32 and d.shape == (g.k,) for _, d in dists)
+    if tolerated == 0:                                                    # tie-free cases: everything is bit-exact
+        assert bank.retrieve_closest_qa_pairs(batch) == g.j["prompts_quant"]
+        assert bank.retrieve_closest_qa_pairs(batch, use_quantifier=False) == g.j["prompts_plain"]
+        assert bank.retrieve_closest_qa_pairs(batch, return_ans=True) == g.j["return_ans"]
+        assert bank.retrieve_closest_qa_pairs(batch, return_info=["question_type"]) == g.j["return_info_type"]
+        assert bank.retrieve_closest_qa_pairs(batch, return_info=["question", "question_id"]) == g.j["return_info_q_id"]
+        assert [list(a) for a, _ in dists] == g.j["return_dists_answers"]
+        for quant, key in ((True, "quant"), (False, "plain")):
+            ids, mask = bank.retrieve_prompt_ids(batch, use_quantifier=quant)
+            assert np.array_equal(ids.cpu().numpy(), g.z[f"input_ids_{key}"])
+            assert np.array_equal(mask.cpu().numpy(), g.z[f"attention_mask_{key}"])
+    else:
+        # duplicates: prompt parity is evaluated on the oracle's vote applied to the accepted index set
+        rows = [[g.answers[j] for j in top[i]] for i in range(g.b)]
+        assert bank.retrieve_closest_qa_pairs(batch) == [O.prompt_sentence(r_, True) for r_ in rows]
+        ids, mask = bank.retrieve_prompt_ids(batch)
+        ids_ref, mask_ref = _oracle_prompt_ids(tokenizer, g.tasks, g.questions, rows, True, 512)
+        assert torch.equal(ids.cpu(), ids_ref) and torch.equal(mask.cpu(), mask_ref)
+    # precedence of the flags (VQAFeatureDataset.py:238-246) and memoisation across the test loop's repeated calls
+    assert bank.retrieve_closest_qa_pairs(batch, return_ans=True, return_dists=True) == \
+        bank.retrieve_closest_qa_pairs(batch, return_ans=True)
+    assert bank._retrieve(batch) is r
+
+
+def test_create_retrieval_dataset_cache_and_additional_data(tmp_path, golden_cases, tokenizer):
+    """A1/A2: build from a loader, write the reference-format cache, reload from it, and append the additional
+    (ROCO-style) bank — the path that crashes in the reference (VQAFeatureDataset.py:181)."""
+    from multimodalpromptretrieval_b200.bank import RetrievalBank
+    from multimodalpromptretrieval_b200 import synthetic as S
+    base = S.make_bank(300, 80, 64, 0.0, seed=1, answers=S.answer_vocab(20, 88))
+    extra = S.make_bank(500, 120, 64, 0.0, seed=2, answers=S.ROCO_ANSWERS, id_prefix="roco")
+    table = {}
+    tok = lambda qs: torch.stack([table[q] for q in qs], 0)
+
+    def loader(bank_, bs=64):
+        for i in range(0, bank_.n, bs):
+            qs = [f"{q} @{j}" for j, q in zip(range(i, i + bs), bank_.info["question"][i:i + bs])]
+            for q, e in zip(qs, bank_.text_half[i:i + bs]):
+                table[q] = e
+            yield {"image": bank_.image_half[i:i + bs], "question": qs, "answer": bank_.answers[i:i + bs],
+                   "question_type": bank_.info["question_type"][i:i + bs],
+                   "question_id": bank_.info["question_id"][i:i + bs]}
+
+    roco_dir = tmp_path / "synthetic_data" / "cache" / "ROCOFeatureDataset"
+    os.makedirs(roco_dir)
+    torch.save(extra.combined(), roco_dir / "embedding.pt")
+    pickle.dump(extra.answers, open(roco_dir / "answers.pkl", "wb"))
+    pickle.dump(extra.info, open(roco_dir / "answer_types.pkl", "wb"))
+    kw = dict(clip_model=_Clip(), clip_tokenize=tok, tokenizer=tokenizer, shard=False, name="VQASLAKEFeatureDataset",
+              cache_root=str(tmp_path / "cache"), additional_root=str(roco_dir))
+    b1 = RetrievalBank(**kw)
+    b1.create_retrieval_dataset(loader(base), "prefix", is_training_phase=False, retrieval_k=5, use_additional_data=True)
+    assert b1.n_total == 800 and len(b1.retrieval_answers) == 800 and len(b1.retrieval_question_info["question"]) == 800
+    assert (tmp_path / "cache" / "VQASLAKEFeatureDataset" / "embedding.pt").exists()
+    cached = torch.load(tmp_path / "cache" / "VQASLAKEFeatureDataset" / "embedding.pt")
+    assert cached.dtype == torch.float32 and tuple(cached.shape) == (300, 128)       # the reference's own format
+    b2 = RetrievalBank(**kw)
+    b2.create_retrieval_dataset(iter(()), "prefix", is_training_phase=False, retrieval_k=5, use_additional_data=True)
+    assert torch.equal(b1.retrieval_embeddings, b2.retrieval_embeddings) and torch.equal(b1.bias, b2.bias)
+    # queries near rows of the appended block must come back with global indices offset by the base size
+    qrows = [310, 555, 799, 3]
+    qs = [f"probe {i}" for i in range(4)]
+    full = torch.cat([base.combined(), extra.combined()], 0)
+    for q, r_ in zip(qs, qrows):
+        table[q] = full[r_, 64:]
+    batch = {"image": full[qrows, :64].clone(), "question": qs, "task": ["Organ"] * 4}
+    got = b2._retrieve(batch)["idx"][:, 0].tolist()
+    assert got == qrows
+    oracle_emb, oracle_ans, oracle_info = O.extend_with_additional_data(
+        base.combined(), base.answers, base.info, extra.combined(), extra.answers, extra.info)
+    expect = O.retrieve_closest_qa_pairs(full[qrows], O.bf16_round(oracle_emb), oracle_ans, oracle_info, 5, False)
+    assert b2.retrieve_closest_qa_pairs(batch) == expect

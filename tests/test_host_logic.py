@@ -1,0 +1,120 @@
+"""CPU tests of the host-side logic and of the C-ABI surface (no compute calls: there is no GPU here)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from multimodalpromptretrieval_b200 import _native, prompt, sharding
+from oracle import retrieval_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_bucket_lut_matches_reference_formula_for_every_m_k():
+    for k in range(1, 33):
+        lut = prompt.bucket_lut(k).reshape(k + 1, k + 1)
+        for n in range(1, k + 1):
+            for m in range(1, n + 1):
+                assert lut[n, m] == O.bucket_index(m, n), (k, n, m)
+    assert prompt.bucket_lut(5).reshape(6, 6)[5, 3] == 3          # 0.6*5 = 3.0000000000000004 -> 3
+    assert prompt.bucket_lut(1)[3] == 5                           # k = 1 is always "certainly" 
+
+
+def test_prompt_string_matches_oracle():
+    for quant in (True, False):
+        for row in (["yes"], ["a", "b", "b"], ["left lung", "x", "left lung", "x", "y"]):
+            ans, m, n = O.vote(row)
+            assert prompt.prompt_string(O.bucket_index(m, n), ans, quant) == O.prompt_sentence(row, quant)
+
+
+def test_tokenisation_by_concatenation_over_whole_vocabulary(tokenizer):
+    """H4: tokens(prefix + retrieved sentence) == tokens(prefix+"I") | tokens(tail) | tokens(bucket) | tokens(answer)."""
+    from multimodalpromptretrieval_b200 import synthetic as S
+    answers = S.answer_vocab(500, 88) + S.ROCO_ANSWERS + ["", "  padded   answer ", "Mixed Case: x?"]
+    segs = prompt.segment_strings(answers)
+    seg_tok = tokenizer(segs, add_special_tokens=False)["input_ids"]
+    questions = S.make_questions(40, 3) + ["", "ends with space ", "what?"]
+    tasks = [S.TASKS[i % len(S.TASKS)] for i in range(len(questions))]
+    for quant in (True, False):
+        pre = tokenizer(prompt.prefix_texts(tasks, questions, quant), add_special_tokens=False)["input_ids"]
+        sents, expect = [], []
+        for qi in range(len(questions)):
+            for ai in range(qi, len(answers), len(questions)):
+                b = (qi + ai) % 6
+                retrieved = prompt.prompt_string(b, answers[ai], quant)
+                sents.append(f"Answer the {tasks[qi]} question: " + questions[qi] + retrieved)
+                tail = seg_tok[prompt.SEG_QUANT] + seg_tok[prompt.SEG_BUCKET0 + b] if quant else seg_tok[prompt.SEG_PLAIN]
+                expect.append(pre[qi] + tail + seg_tok[prompt.SEG_ANSWER0 + ai] + [tokenizer.eos_token_id])
+        got = tokenizer(sents, add_special_tokens=True)["input_ids"]
+        assert got == expect
+
+
+def test_shard_bounds_partition_rows():
+    for n in (0, 1, 7, 128, 1000, 10_000_000):
+        for w in (1, 2, 3, 4, 8):
+            spans = [sharding.shard_bounds(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert all(0 <= e - b <= -(-n // w) for b, e in spans)
+            if n:
+                for row in (0, n // 2, n - 1):
+                    r = sharding.owner_of_row(row, n, w)
+                    assert spans[r][0] <= row < spans[r][1]
+    with pytest.raises(ValueError):
+        sharding.shard_bounds(10, 2, 2)
+
+
+def test_key_encoding_orders_by_score_then_lower_row():
+    score = np.array([[1.5, 1.5, -2.0, 0.0, -0.0, 3.25, -np.inf]], dtype=np.float32)
+    idx = np.array([[7, 3, 1, 2, 9, 5, 4]], dtype=np.int32)
+    keys = O.keys_from(score, idx)
+    order = np.argsort(-keys.astype(np.float64), kind="stable")  # only for a rough look; exact check below
+    srt = sorted(range(7), key=lambda i: (-score[0, i], idx[0, i]))
+    exact = sorted(range(7), key=lambda i: int(keys[0, i]), reverse=True)
+    # +0.0 and -0.0 differ in the ordered image (-0.0 < +0.0); everything else follows (score desc, row asc)
+    assert [i for i in exact if i not in (3, 4)] == [i for i in srt if i not in (3, 4)]
+    s2, i2 = O.decode_keys(keys)
+    assert np.array_equal(s2.view(np.uint32), score.view(np.uint32)) and np.array_equal(i2, idx)
+    merged = O.merge_keys(np.stack([keys[:, :4], keys[:, 3:7]], 0), 3)
+    assert [int(x) for x in O.decode_keys(merged)[1][0]] == [5, 3, 7]
+    del order
+
+
+def test_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "multimodalpromptretrieval_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+                assert "retrieval_oracle" not in src, f
+
+
+def test_c_abi_library_loads_and_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "mpr_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(mpr_[a-z_]+)\s*\(", header)))
+    assert declared == sorted(_native.EXPORTS)
+    assert os.path.exists(_native.LIB_PATH), "run __graft_entry__.build() first"
+    lib = ctypes.CDLL(_native.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    lib.mpr_abi_version.restype = ctypes.c_int
+    assert lib.mpr_abi_version() == 1
+
+
+def test_no_fallback_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from multimodalpromptretrieval_b200 import kernels
+    from multimodalpromptretrieval_b200.bank import RetrievalBank
+    with pytest.raises(_native.NativeError):
+        kernels.handle()
+    with pytest.raises(RuntimeError):
+        RetrievalBank()
+    # mpr_create itself refuses: no device, no handle
+    lib = _native.load()
+    h = ctypes.c_void_p()
+    assert lib.mpr_create(0, ctypes.byref(h)) != 0 and not h.value
