@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""Benchmark of the retrieval hot path (BASELINE.json metric: retrieval queries/sec, 512-d, top-k).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            this repo's CUDA path
+    python bench.py --impl reference [--gpus N] --steps K --warmup W   the reference's CPU ops on the host cores
+
+Workload (cfg5 point of BASELINE.json, the one north_star's target is quoted on): a 10 M-row x 512-d bf16 bank,
+row-sharded over the N GPUs of one box (STRONG scaling: the bank is fixed, each rank scans 10M/N rows), one batch of
+128 queries per step, k = 5.  A step = query cast (kernel 1) -> bank scan with fused top-k (kernel 2) -> split merge
+(kernel 4) -> [NCCL all-gather of the candidates -> kernel 4] -> vote + prompt-token gather (kernel 3).
+
+  value   queries/s with the step's inputs already in HBM (CUDA events, barrier + synchronize both sides, max over ranks)
+  e2e     the same step through the public host API (RetrievalBank.retrieve_prompt_ids) with HOST inputs: pinned-memory
+          query embeddings copied H2D, prefix tokenisation on the host, prompt ids / mask copied D2H, every step
+  roofline  scan kernel: algorithmic bytes (N_local*D*2 + N_local*4) / its mean launch time (cudaEvents around the
+          kernel on its own stream, via mpr_profile_begin/end) against the measured HBM copy bandwidth
+  cpu_baseline  the reference's torch.cdist + torch.argsort on the host cores, on a bounded sample (N = 1 only)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "retrieval queries/sec (512-d, top-k)"
+UNIT = "queries/s"
+BANK_ROWS = 10_000_000
+DIM = 512
+BATCH = 128
+TOPK = 5
+GEN_CHUNK = 250_000
+N_ANSWERS = 24           # ROCO synthetic-QA answer vocabulary
+CPU_SAMPLE_ROWS = 250_000
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--bank-rows", type=int, default=BANK_ROWS)
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--k", type=int, default=TOPK)
+    ap.add_argument("--dim", type=int, default=DIM)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(args, n_gpus):
+    return {
+        "workload": f"cfg5: {args.bank_rows:,} x {args.dim} bf16 bank row-sharded over {n_gpus} GPU(s), "
+                    f"batch {args.batch}, k={args.k} (L2-distance ranking on un-normalised rows, test phase)",
+        "bank_rows": args.bank_rows, "dim": args.dim, "batch": args.batch, "k": args.k,
+        "rows_per_gpu": -(-args.bank_rows // n_gpus), "parallelism": f"bank-row shards x{n_gpus}",
+        "cache": "inputs larger than L2 (per-GPU shard >= 1.28 GB vs 126 MB L2); no flush needed",
+    }
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.samples, self.proc, self.thread = [], None, None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.QUERY}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [l.split(", ") for t, l in self.samples if t0 - 0.05 <= t <= t1 + 0.15] or \
+               [l.split(", ") for _, l in self.samples[-3:]]
+        if not rows:
+            return None
+        try:
+            sm = sorted(float(r[0]) for r in rows)
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            reasons = [n for i, n in enumerate(names) if any(r[3 + i].strip().lower() == "active" for r in rows)]
+            return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "reasons": reasons,
+                    "power_w_max": max(float(r[2]) for r in rows), "samples": len(rows)}
+        except Exception:
+            return None
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def run_reference_arm(args, rank: int, n_gpus: int):
+    """The reference's CPU implementation of the path (torch.cdist + torch.argsort + slice,
+    /root/reference/dataset/VQAFeatureDataset.py:192-197, restated in oracle/retrieval_oracle.py) on the host cores."""
+    if rank != 0:
+        return
+    import torch
+    from oracle import retrieval_oracle as O
+    threads = torch.get_num_threads()
+    sample_rows = min(CPU_SAMPLE_ROWS, args.bank_rows)
+    g = torch.Generator().manual_seed(88)
+    bank = torch.randn(sample_rows, args.dim, generator=g) * (10.0 / args.dim ** 0.5)
+    q = torch.randn(args.batch, args.dim, generator=g) * (10.0 / args.dim ** 0.5)
+    scale = args.bank_rows / sample_rows
+
+    def step():
+        return O.reference_ops_topk(q, bank, args.k, False)
+
+    t = time.perf_counter()
+    step()
+    first = time.perf_counter() - t
+    # keep the whole run inside a few minutes whatever --steps says
+    budget = 150.0
+    steps, warm = args.steps, args.warmup
+    if first * (steps + warm) > budget:
+        shrink = max(0.02, budget / (first * (steps + warm)))
+        sample_rows = max(10_000, int(sample_rows * shrink))
+        bank = bank[:sample_rows].contiguous()
+        scale = args.bank_rows / sample_rows
+    for _ in range(warm):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    ms = dt / steps * 1e3
+    value = args.batch / (ms * 1e-3 * scale)        # the ops are linear in bank rows: scale the sample to the full bank
+    sample = (f"{args.batch} queries x {sample_rows:,}-row fp32 sample of the {args.bank_rows:,}-row bank per step, "
+              f"time scaled x{scale:.1f} (cdist and argsort are linear in bank rows)")
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": ms * scale, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "fp32", "data": "synthetic", "config": workload_config(args, n_gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "host": {"cpu_count": os.cpu_count(), "torch_threads": threads},
+    }
+    print(json.dumps(out), flush=True)
+
+
+def cpu_baseline(args):
+    """Bounded CPU sample next to the GPU number (rank 0, N = 1): ~10-30 s of host work."""
+    import torch
+    from oracle import retrieval_oracle as O
+    threads = torch.get_num_threads()
+    rows = min(CPU_SAMPLE_ROWS, args.bank_rows)
+    g = torch.Generator().manual_seed(88)
+    bank = torch.randn(rows, args.dim, generator=g) * (10.0 / args.dim ** 0.5)
+    q = torch.randn(args.batch, args.dim, generator=g) * (10.0 / args.dim ** 0.5)
+    O.reference_ops_topk(q, bank, args.k, False)
+    t0 = time.perf_counter()
+    reps = 0
+    while reps < 3 or (time.perf_counter() - t0 < 10.0 and reps < 20):
+        O.reference_ops_topk(q, bank, args.k, False)
+        reps += 1
+    dt = (time.perf_counter() - t0) / reps
+    scale = args.bank_rows / rows
+    return {"value": args.batch / (dt * scale), "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"torch.cdist+argsort (VQAFeatureDataset.py:192-197), {args.batch} queries x {rows:,}-row fp32 "
+                      f"sample, {reps} reps, {dt * 1e3:.0f} ms each, scaled x{scale:.0f} to {args.bank_rows:,} rows",
+            "host_cpu_count": os.cpu_count()}
+
+
+# ------------------------------------------------------------------------------------------------ native arm
+def run_native(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    n_gpus = max(args.gpus, world)
+    torch.cuda.set_device(local_rank)
+    dev = torch.device(f"cuda:{local_rank}")
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from multimodalpromptretrieval_b200 import kernels as K
+    from multimodalpromptretrieval_b200 import synthetic as S
+    from multimodalpromptretrieval_b200.bank import LazyPart, RetrievalBank
+
+    class PassThroughClip:
+        """CLIP's forward is out of scope (stock PyTorch); the 'image' tensor already carries the 512-d embedding."""
+        encode_image = staticmethod(lambda x: x)
+        encode_text = staticmethod(lambda x: None)
+
+    tokenizer = S.load_tokenizer(os.path.join(ROOT, "tests", "golden", "spm"))
+    bank = RetrievalBank(clip_model=PassThroughClip(), clip_tokenize=None, tokenizer=tokenizer, device=dev,
+                         memoise=False)
+    bank.clip_tokenize = lambda qs: None
+
+    # ---- synthetic bank: chunk c is seeded by c, so the bank's contents do not depend on the GPU count
+    n, d = args.bank_rows, args.dim
+    scale = 10.0 / d ** 0.5
+
+    def chunk_fn(c, rows):
+        def fn():
+            g = torch.Generator(device=dev).manual_seed(88 + c)
+            return torch.randn(rows, d, device=dev, generator=g) * scale, None
+        return fn
+
+    parts = [LazyPart(min(GEN_CHUNK, n - c0), d, chunk_fn(c0 // GEN_CHUNK, min(GEN_CHUNK, n - c0)))
+             for c0 in range(0, n, GEN_CHUNK)]
+    answer_ids = (np.arange(n, dtype=np.int64) * 2654435761 % 4294967296 >> 7) % N_ANSWERS
+    bank.install_bank(parts, None, None, is_training_phase=False, retrieval_k=args.k,
+                      answer_ids=answer_ids.astype(np.int32), answer_strings=S.ROCO_ANSWERS[:N_ANSWERS])
+    n_local = bank.retrieval_embeddings.shape[0]
+    kk = args.k
+
+    # ---- queries: half near-copies of bank rows (so the top-1 is meaningful), half fresh
+    b = args.batch
+    g = torch.Generator().manual_seed(89)
+    q_host = (torch.randn(b, d, generator=g) * scale).pin_memory()
+    questions = [f"{q} #{i}" for i, q in enumerate(S.make_questions(b, 96))]
+    tasks = [S.TASKS[i % len(S.TASKS)] for i in range(b)]
+    q_dev = q_host.to(dev)
+    tables = bank._prompt_tables()
+    pre_ids, pre_off, longest = tables.prefixes(tasks, questions, True)
+    stride = min(512, longest + tables.tail_bound(True))
+    lut = bank._lut(args.k)
+
+    def device_step():
+        res = bank.search_embeddings(q_dev, None, kk=kk)
+        return K.prompt_gather(res["idx"], 0, bank.answer_id, lut, pre_ids, pre_off, tables.seg_ids, tables.seg_off,
+                               True, tables.pad_id, tables.eos_id, 512, stride)
+
+    def e2e_step():
+        batch = {"image": q_host, "question": questions, "task": tasks}
+        ids, mask = bank.retrieve_prompt_ids(batch, use_quantifier=True)
+        return ids.cpu(), mask.cpu()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, profile=False):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        if profile:
+            K.profile_begin(steps + 2, dev.index)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.time()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        t1 = time.time()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        scan = K.profile_end(dev.index) if profile else (0.0, 0)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item() / steps, scan, (t0, t1)
+
+    out0 = device_step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms_step, (scan_ms, scan_n), (t0, t1) = timed(device_step, args.steps, max(args.warmup, 3), profile=True)
+    clocks = sampler.stop(t0, t1) if sampler else None
+    e2e_steps = max(5, min(args.steps, 50))
+    ms_e2e, _, _ = timed(e2e_step, e2e_steps, 3)
+    ids_h, mask_h = e2e_step()
+    if K.handle(dev.index).device_error() != 0:
+        raise RuntimeError("device-side pipeline error during the benchmark")
+
+    # ---- roofline of the scan kernel (this rank's shard)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    alg_bytes = n_local * d * 2 + n_local * 4
+    scan_avg_ms = scan_ms / max(scan_n, 1)
+    achieved = alg_bytes / (scan_avg_ms * 1e-3) / 1e9 if scan_n else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "scan_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            tj = json.load(open(tpath))
+            if tj.get("rows_per_gpu") == n_local and tj.get("batch") == b:
+                traffic = tj.get("dram_bytes_per_launch")
+        except Exception:
+            pass
+    roofline = {"bound": "hbm", "kernel": "scan_topk_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": scan_avg_ms, "launches_timed": scan_n,
+                "share_of_step": scan_avg_ms / ms_step if ms_step else None}
+
+    if rank == 0:
+        launches_per_step = 4 + (1 if world > 1 else 0)   # bank_build(q), scan, merge, [merge], prompt_gather
+        h2d = q_host.numel() * 4 + int(pre_ids.numel() + pre_off.numel()) * 4
+        d2h = int(ids_h.numel() + mask_h.numel()) * 8 + 4
+        result = {
+            "metric": METRIC, "value": b / (ms_step * 1e-3), "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args, n_gpus),
+            "clocks": clocks,
+            "e2e": {"value": b / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e, "steps": e2e_steps,
+                    "api": "RetrievalBank.retrieve_prompt_ids(batch) with pinned host embeddings + .cpu() of ids/mask"},
+            "gpu_launches": launches_per_step * args.steps,
+            "gpu_launches_per_step": launches_per_step,
+            "roofline": roofline,
+            "plan": K.search_plan(b, n_local, d, kk, dev.index),
+            "sample_output": {"prompt_tokens": int(out0["length"].max().item()),
+                              "majority_answer0": S.ROCO_ANSWERS[int(out0["majority_answer"][0].item())]},
+        }
+        if n_gpus == 1 and not args.no_cpu_baseline:
+            result["cpu_baseline"] = cpu_baseline(args)
+        print(json.dumps(result), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, max(args.gpus, world))
+        return
+    run_native(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -107,6 +107,14 @@ int mpr_prompt_gather(mpr_handle_t h, const int32_t* idx, int b, int kk, int ski
 int mpr_debug_scores(mpr_handle_t h, const uint16_t* q, int b, const uint16_t* bank, const float* bias,
                      int64_t n_local, int d, float* scores, void* workspace, size_t workspace_bytes, void* stream);
 
+/*
+ * Measurement aid for bench.py's roofline: between begin and end every scan-kernel launch (kernel 2 only, not the
+ * merge) is bracketed by a cudaEvent pair on the launching stream.  mpr_profile_end synchronises on the last event and
+ * returns the summed device time and the number of launches.  At most max_launches launches are recorded.
+ */
+int mpr_profile_begin(mpr_handle_t h, int max_launches);
+int mpr_profile_end(mpr_handle_t h, float* total_ms, int* n_launches);
+
 /* Launch geometry the library would use for a shape (for bench/roofline bookkeeping). */
 int mpr_search_plan(mpr_handle_t h, int b, int64_t n_local, int d, int kk, int* n_ctas, int* n_splits,
                     int* n_qtiles, int* n_stages, int* smem_bytes);

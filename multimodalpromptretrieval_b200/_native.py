@@ -18,7 +18,7 @@ SRC_F32, SRC_F16, SRC_BF16 = 0, 1, 2
 EXPORTS = [
     "mpr_abi_version", "mpr_create", "mpr_destroy", "mpr_last_error", "mpr_device_error", "mpr_bank_build",
     "mpr_search_workspace_bytes", "mpr_search_topk", "mpr_merge_topk", "mpr_prompt_gather", "mpr_debug_scores",
-    "mpr_search_plan",
+    "mpr_search_plan", "mpr_profile_begin", "mpr_profile_end",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -64,6 +64,10 @@ def load() -> C.CDLL:
     lib.mpr_debug_scores.argtypes = [vp, vp, i32, vp, vp, i64, i32, vp, vp, sz, vp]
     lib.mpr_search_plan.restype = i32
     lib.mpr_search_plan.argtypes = [vp, i32, i64, i32, i32] + [C.POINTER(i32)] * 5
+    lib.mpr_profile_begin.restype = i32
+    lib.mpr_profile_begin.argtypes = [vp, i32]
+    lib.mpr_profile_end.restype = i32
+    lib.mpr_profile_end.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(i32)]
     _lib = lib
     return lib
 

@@ -29,6 +29,27 @@ from .sharding import CandidateExchange, shard_bounds
 _INFO_KEYS = ("question_type", "question_id", "question")
 
 
+class LazyPart:
+    """A block of ``n_rows`` bank rows produced on demand by ``fn() -> (a, b_or_None)``; only called on the ranks
+    whose shard overlaps the block (lets every rank of a sharded job materialise just its own rows)."""
+
+    def __init__(self, n_rows: int, dim: int, fn):
+        self.n_rows, self.dim, self.fn = int(n_rows), int(dim), fn
+
+
+class _AnswerView:
+    """``retrieval_answers`` for banks installed from pre-interned ids: a read-only sequence of strings."""
+
+    def __init__(self, ids: np.ndarray, strings: Sequence[str]):
+        self.ids, self.strings = ids, strings
+
+    def __len__(self):
+        return len(self.ids)
+
+    def __getitem__(self, i):
+        return self.strings[int(self.ids[i])]
+
+
 class RetrievalBank:
     def __init__(self, clip_model=None, clip_tokenize=None, tokenizer=None, device=None, normalise: bool = False,
                  process_group=None, shard: bool = True, max_source_length: int = 512, name: str = "VQADataset",
@@ -125,53 +146,65 @@ class RetrievalBank:
         print(f"Retrieval features shape: {torch.Size([self.n_total, self.dim])}")
         print(f"Number of answers: {len(self.retrieval_answers)}")
 
-    def install_bank(self, parts: Iterable[Tuple[torch.Tensor, Optional[torch.Tensor]]], answers: Sequence[str],
-                     info: Dict[str, Sequence[str]], is_training_phase: Optional[bool] = None,
-                     retrieval_k: Optional[int] = None) -> None:
+    def install_bank(self, parts: Iterable, answers: Optional[Sequence[str]], info: Optional[Dict[str, Sequence[str]]],
+                     is_training_phase: Optional[bool] = None, retrieval_k: Optional[int] = None,
+                     answer_ids: Optional[np.ndarray] = None, answer_strings: Optional[Sequence[str]] = None) -> None:
         """Lays the bank out in HBM.  ``parts`` is a sequence of row blocks in global row order, each either
-        ``(combined [n, D], None)`` or ``(image_half [n, d0], text_half [n, d1])``, fp32/fp16/bf16, on any device.
-        Kernel 1 casts (and optionally normalises) every block straight into this rank's bf16 shard."""
+        ``(combined [n, D], None)``, ``(image_half [n, d0], text_half [n, d1])`` (fp32/fp16/bf16, any device) or a
+        :class:`LazyPart`.  Kernel 1 casts (and optionally normalises) every block straight into this rank's bf16
+        shard.  Answers are either a list of N strings or pre-interned (``answer_ids`` int32 [N] + ``answer_strings``)."""
         if is_training_phase is not None:
             self.is_training_phase = is_training_phase
         if retrieval_k is not None:
             self.retrieval_k = retrieval_k
         parts = list(parts)
-        n_total = sum(int(p[0].shape[0]) for p in parts)
+        rows_of = lambda p: p.n_rows if isinstance(p, LazyPart) else int(p[0].shape[0])
+        n_total = sum(rows_of(p) for p in parts)
         if n_total == 0:
             raise ValueError("empty retrieval bank")
-        dim = int(parts[0][0].shape[1] + (parts[0][1].shape[1] if parts[0][1] is not None else 0))
-        if len(answers) != n_total:
-            raise ValueError(f"{len(answers)} answers for {n_total} bank rows")
+        p0 = parts[0]
+        dim = p0.dim if isinstance(p0, LazyPart) else int(p0[0].shape[1] + (p0[1].shape[1] if p0[1] is not None else 0))
+        n_answers = len(answers) if answers is not None else len(answer_ids)
+        if n_answers != n_total:
+            raise ValueError(f"{n_answers} answers for {n_total} bank rows")
         begin, end = shard_bounds(n_total, self.exchange.rank, self.exchange.world_size)
         n_local = end - begin
         bank = torch.empty((max(n_local, 1), dim), dtype=torch.bfloat16, device=self.device)[:n_local]
         bias = torch.empty((max(n_local, 1),), dtype=torch.float32, device=self.device)[:n_local]
         row = 0
         chunk_rows = max(1, (256 << 20) // (dim * 4))       # stage host blocks through <= 256 MiB device buffers
-        for a, b in parts:
-            n = int(a.shape[0])
+        for part in parts:
+            n = rows_of(part)
             lo, hi = max(begin, row), min(end, row + n)
-            for c0 in range(lo, hi, chunk_rows):
-                c1 = min(hi, c0 + chunk_rows)
-                sa = a[c0 - row:c1 - row].to(self.device, non_blocking=True).contiguous()
-                sb = None if b is None else b[c0 - row:c1 - row].to(self.device, non_blocking=True).contiguous()
-                if sa.dtype not in (torch.float32, torch.float16, torch.bfloat16):
-                    sa = sa.float()
-                    sb = None if sb is None else sb.float()
-                K.bank_build(sa, sb, normalise=self.normalise, out=bank[c0 - begin:c1 - begin],
-                             bias=bias[c0 - begin:c1 - begin])
+            if lo < hi:
+                a, b = part.fn() if isinstance(part, LazyPart) else part
+                for c0 in range(lo, hi, chunk_rows):
+                    c1 = min(hi, c0 + chunk_rows)
+                    sa = a[c0 - row:c1 - row].to(self.device, non_blocking=True).contiguous()
+                    sb = None if b is None else b[c0 - row:c1 - row].to(self.device, non_blocking=True).contiguous()
+                    if sa.dtype not in (torch.float32, torch.float16, torch.bfloat16):
+                        sa = sa.float()
+                        sb = None if sb is None else sb.float()
+                    K.bank_build(sa, sb, normalise=self.normalise, out=bank[c0 - begin:c1 - begin],
+                                 bias=bias[c0 - begin:c1 - begin])
+                del a, b
             row += n
         self.retrieval_embeddings = bank
         self.bias = bias
         self.n_total, self.dim, self.row_begin = n_total, dim, begin
-        self.retrieval_answers = list(answers)
-        self.retrieval_question_info = {k: list(v) for k, v in info.items()}
-        # intern the answers: bank row -> answer id, replicated on every rank (4 B/row)
-        table: Dict[str, int] = {}
-        ids = np.empty(n_total, dtype=np.int32)
-        for i, a in enumerate(self.retrieval_answers):
-            ids[i] = table.setdefault(a, len(table))
-        self.answer_strings = list(table.keys())
+        self.retrieval_question_info = {k: list(v) for k, v in (info or {}).items()}
+        if answers is not None:
+            # intern the answers: bank row -> answer id, replicated on every rank (4 B/row)
+            self.retrieval_answers = list(answers)
+            table: Dict[str, int] = {}
+            ids = np.empty(n_total, dtype=np.int32)
+            for i, a in enumerate(self.retrieval_answers):
+                ids[i] = table.setdefault(a, len(table))
+            self.answer_strings = list(table.keys())
+        else:
+            ids = np.ascontiguousarray(answer_ids, dtype=np.int32)
+            self.answer_strings = list(answer_strings)
+            self.retrieval_answers = _AnswerView(ids, self.answer_strings)
         self.answer_id = torch.from_numpy(ids).to(self.device)
         self._tables = None
         self._memo = None
@@ -179,12 +212,12 @@ class RetrievalBank:
     # ------------------------------------------------------------------------------------------ query path
     def _encode(self, batch) -> Tuple[torch.Tensor, torch.Tensor]:
         """The two CLIP calls of VQAFeatureDataset.py:146-147 / :189-190 (stock PyTorch, out of scope)."""
-        img = self.clip_model.encode_image(batch["image"].to(self.device))
+        img = self.clip_model.encode_image(batch["image"].to(self.device, non_blocking=True))
         tokens = self.clip_tokenize(batch["question"]) if self.clip_tokenize is not None else batch["question"]
         if isinstance(tokens, torch.Tensor):
-            tokens = tokens.to(self.device)
+            tokens = tokens.to(self.device, non_blocking=True)
         txt = self.clip_model.encode_text(tokens)
-        return img.detach().contiguous(), txt.detach().contiguous()
+        return img.detach().contiguous(), (None if txt is None else txt.detach().contiguous())
 
     def search_embeddings(self, image_half: torch.Tensor, text_half: Optional[torch.Tensor] = None, kk: Optional[int] = None
                           ) -> Dict[str, torch.Tensor]:
@@ -236,14 +269,7 @@ class RetrievalBank:
         with torch.no_grad():
             img, txt = self._encode(batch)
         res = self.search_embeddings(img, txt, kk=k + skip)
-        # vote on the device (kernel 3 without tokens needs no tokenizer: empty segment tables)
-        out = {"skip": skip, "k": k, "device": res}
-        idx_h = res["idx"].cpu().numpy()
-        score_h = res["score"].cpu().numpy()
-        qsq_h = res["q_sqnorm"].cpu().numpy()
-        out["idx"] = idx_h
-        out["score"] = score_h
-        out["q_sqnorm"] = qsq_h
+        out = {"skip": skip, "k": k, "device": res}       # everything stays on the device until somebody asks
         if self.memoise:
             try:
                 self._memo = (weakref.ref(img_t), list(batch["question"]), out)
@@ -251,10 +277,20 @@ class RetrievalBank:
                 self._memo = None
         return out
 
+    @staticmethod
+    def _host(r: dict) -> dict:
+        """Single D2H of the search result (replaces the reference's B*k ``tensor.__index__`` syncs at :199)."""
+        if "idx" not in r:
+            res = r["device"]
+            r["idx"] = res["idx"].cpu().numpy()
+            r["score"] = res["score"].cpu().numpy()
+            r["q_sqnorm"] = res["q_sqnorm"].cpu().numpy()
+        return r
+
     def retrieve_closest_qa_pairs(self, batch, return_ans: bool = False, return_info=None, return_dists: bool = False,
                                   use_quantifier: bool = True):
         """Same contract as VQAFeatureDataset.py:187-246 (precedence return_ans > return_info > return_dists)."""
-        r = self._retrieve(batch)
+        r = self._host(self._retrieve(batch))
         skip, k = r["skip"], r["k"]
         top = r["idx"][:, skip:skip + k]
         answers = [[self.retrieval_answers[int(x)] for x in row if x >= 0] for row in top]            # :199

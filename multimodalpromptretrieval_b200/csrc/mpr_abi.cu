@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstring>
 #include <numeric>
+#include <vector>
 
 #include "../../include/mpr_b200.h"
 #include "bank_build.cuh"
@@ -25,6 +26,8 @@ struct mpr_context {
     int num_sms = 0;
     int* d_err = nullptr;
     PFN_encodeTiled encode = nullptr;
+    std::vector<cudaEvent_t> prof_events;   // start/stop pairs, used only between mpr_profile_begin/end
+    int prof_used = -1;                     // -1 = profiling off
     char err[512] = {0};
 };
 
@@ -142,8 +145,14 @@ static int launch_scan(mpr_context* h, const ScanPlan& pl, const uint16_t* q, in
     p.err = h->d_err;
 
     const dim3 grid(pl.n_splits * pl.n_qtiles);
+    const bool prof = h->prof_used >= 0 && 2 * (h->prof_used + 1) <= static_cast<int>(h->prof_events.size());
+    if (prof) CUDA_TRY(h, cudaEventRecord(h->prof_events[2 * h->prof_used], st));
     scan_topk_kernel<kDump><<<grid, kScanThreads, pl.smem_bytes, st>>>(tq, tb, p);
     CUDA_TRY(h, cudaGetLastError());
+    if (prof) {
+        CUDA_TRY(h, cudaEventRecord(h->prof_events[2 * h->prof_used + 1], st));
+        ++h->prof_used;
+    }
     return MPR_OK;
 }
 
@@ -190,8 +199,36 @@ int mpr_create(int device, mpr_handle_t* out) {
     return MPR_OK;
 }
 
+int mpr_profile_begin(mpr_handle_t h, int max_launches) {
+    if (!h || max_launches < 1) return fail(h, MPR_EINVAL, "bad arguments");
+    while (static_cast<int>(h->prof_events.size()) < 2 * max_launches) {
+        cudaEvent_t e;
+        CUDA_TRY(h, cudaEventCreate(&e));
+        h->prof_events.push_back(e);
+    }
+    h->prof_used = 0;
+    return MPR_OK;
+}
+
+int mpr_profile_end(mpr_handle_t h, float* total_ms, int* n_launches) {
+    if (!h || !total_ms || !n_launches) return fail(h, MPR_EINVAL, "null argument");
+    const int n = h->prof_used < 0 ? 0 : h->prof_used;
+    h->prof_used = -1;
+    float total = 0.f;
+    if (n > 0) CUDA_TRY(h, cudaEventSynchronize(h->prof_events[2 * n - 1]));
+    for (int i = 0; i < n; ++i) {
+        float ms = 0.f;
+        CUDA_TRY(h, cudaEventElapsedTime(&ms, h->prof_events[2 * i], h->prof_events[2 * i + 1]));
+        total += ms;
+    }
+    *total_ms = total;
+    *n_launches = n;
+    return MPR_OK;
+}
+
 int mpr_destroy(mpr_handle_t h) {
     if (!h) return MPR_OK;
+    for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
     if (h->d_err) cudaFree(h->d_err);
     delete h;
     return MPR_OK;

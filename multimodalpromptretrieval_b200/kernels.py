@@ -166,3 +166,16 @@ def debug_scores(q: torch.Tensor, bank: torch.Tensor, bias: torch.Tensor) -> tor
                                 _stream())
     h.check(rc, "mpr_debug_scores")
     return scores
+
+
+def profile_begin(max_launches: int, device: Optional[int] = None) -> None:
+    h = handle(device)
+    h.check(h.lib.mpr_profile_begin(h.ptr, max_launches), "mpr_profile_begin")
+
+
+def profile_end(device: Optional[int] = None) -> Tuple[float, int]:
+    """(summed scan-kernel device time in ms, launches recorded) since :func:`profile_begin`."""
+    h = handle(device)
+    ms, n = C.c_float(0), C.c_int(0)
+    h.check(h.lib.mpr_profile_end(h.ptr, C.byref(ms), C.byref(n)), "mpr_profile_end")
+    return ms.value, n.value

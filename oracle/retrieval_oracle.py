@@ -194,3 +194,15 @@ def decode_keys(keys: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
     score = bits.view(np.float32)
     idx = np.where(keys == 0, -1, (~(keys & np.uint64(0xFFFFFFFF)).astype(np.uint32)).astype(np.int64)).astype(np.int32)
     return score, idx
+
+
+# --------------------------------------------------------------------------------------------- CPU baseline
+def reference_ops_topk(combined: torch.Tensor, retrieval_embeddings: torch.Tensor, retrieval_k: int,
+                       is_training_phase: bool) -> torch.Tensor:
+    """The reference's scoring + selection exactly as shipped — ``torch.cdist`` then the default (unstable)
+    ``torch.argsort`` and the slice (VQAFeatureDataset.py:192-197).  This is what ``bench.py`` times as the CPU
+    baseline / ``--impl reference`` arm; it is never used as a checker (ties are implementation-defined)."""
+    dist_matrix = torch.cdist(combined.float(), retrieval_embeddings)
+    if is_training_phase:
+        return torch.argsort(dist_matrix, axis=1)[:, 1:1 + retrieval_k]
+    return torch.argsort(dist_matrix, axis=1)[:, 0:retrieval_k]

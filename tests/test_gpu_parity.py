@@ -304,7 +304,7 @@ def _bank_from_golden(g, tokenizer, **kw):
 def test_retrieval_bank_reproduces_reference_golden(name, golden_cases, tokenizer):
     g = golden_cases[name]
     bank, batch = _bank_from_golden(g, tokenizer)
-    r = bank._retrieve(batch)
+    r = bank._host(bank._retrieve(batch))
     s_ref = O.scores_f64(g.queries(), g.bank())
     skip = 1 if g.training else 0
     top = r["idx"][:, skip:skip + g.k].astype(np.int64)
@@ -378,7 +378,7 @@ def test_create_retrieval_dataset_cache_and_additional_data(tmp_path, golden_cas
     for q, r_ in zip(qs, qrows):
         table[q] = full[r_, 64:]
     batch = {"image": full[qrows, :64].clone(), "question": qs, "task": ["Organ"] * 4}
-    got = b2._retrieve(batch)["idx"][:, 0].tolist()
+    got = b2._host(b2._retrieve(batch))["idx"][:, 0].tolist()
     assert got == qrows
     oracle_emb, oracle_ans, oracle_info = O.extend_with_additional_data(
         base.combined(), base.answers, base.info, extra.combined(), extra.answers, extra.info)
