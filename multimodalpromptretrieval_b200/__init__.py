@@ -5,3 +5,10 @@ answer vote / prompt-token gather.  Hand-written sm_100a CUDA behind a C ABI (``
 the host mirror of the reference's ``VQADataset.create_retrieval_dataset`` / ``retrieve_closest_qa_pairs``.
 """
 __version__ = "0.1.0"
+
+
+def __getattr__(name):   # lazy: importing the package must not require torch/CUDA (build(), CPU tests)
+    if name == "RetrievalBank":
+        from .bank import RetrievalBank
+        return RetrievalBank
+    raise AttributeError(name)
