@@ -114,6 +114,8 @@ int mpr_debug_scores(mpr_handle_t h, const uint16_t* q, int b, const uint16_t* b
  */
 int mpr_profile_begin(mpr_handle_t h, int max_launches);
 int mpr_profile_end(mpr_handle_t h, float* total_ms, int* n_launches);
+/* Device time of the i-th launch recorded by the last begin/end pair (valid after mpr_profile_end). */
+int mpr_profile_launch_ms(mpr_handle_t h, int i, float* ms);
 
 /* Launch geometry the library would use for a shape (for bench/roofline bookkeeping). */
 int mpr_search_plan(mpr_handle_t h, int b, int64_t n_local, int d, int kk, int* n_ctas, int* n_splits,

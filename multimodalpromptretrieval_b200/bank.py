@@ -50,12 +50,40 @@ class _AnswerView:
         return self.strings[int(self.ids[i])]
 
 
+class _SearchGraph:
+    """One captured search chain for fixed (batch, dims, dtype, k+skip): static input/output buffers + a CUDAGraph."""
+
+    def __init__(self, bank: "RetrievalBank", img: torch.Tensor, txt: Optional[torch.Tensor], kk: int):
+        self.img = torch.empty_like(img)
+        self.txt = None if txt is None else torch.empty_like(txt)
+        self.img.copy_(img)
+        if txt is not None:
+            self.txt.copy_(txt)
+        side = torch.cuda.Stream(device=bank.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                       # warm-up outside capture (allocations, NCCL communicator)
+            for _ in range(2):
+                bank.search_embeddings(self.img, self.txt, kk=kk)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = bank.search_embeddings(self.img, self.txt, kk=kk)
+
+    def run(self, img: torch.Tensor, txt: Optional[torch.Tensor]) -> Dict[str, torch.Tensor]:
+        self.img.copy_(img, non_blocking=True)
+        if txt is not None:
+            self.txt.copy_(txt, non_blocking=True)
+        self.graph.replay()
+        return self.out
+
+
 class RetrievalBank:
     def __init__(self, clip_model=None, clip_tokenize=None, tokenizer=None, device=None, normalise: bool = False,
                  process_group=None, shard: bool = True, max_source_length: int = 512, name: str = "VQADataset",
                  cache_root: str = "cache", additional_root: str = os.path.join("synthetic_data", "cache",
                                                                                "ROCOFeatureDataset"),
-                 memoise: bool = True):
+                 memoise: bool = True, use_cuda_graph: bool = False):
         if not torch.cuda.is_available():
             raise RuntimeError("RetrievalBank needs a B200 (sm_100a) GPU; there is no CPU fallback path")
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
@@ -68,6 +96,8 @@ class RetrievalBank:
         self.cache_root = cache_root
         self.additional_root = additional_root
         self.memoise = memoise
+        self.use_cuda_graph = bool(use_cuda_graph)
+        self._graphs: Dict[tuple, "_SearchGraph"] = {}
         self.exchange = CandidateExchange(process_group if shard else None)
         if not shard:
             self.exchange.rank, self.exchange.world_size = 0, 1
@@ -208,6 +238,7 @@ class RetrievalBank:
         self.answer_id = torch.from_numpy(ids).to(self.device)
         self._tables = None
         self._memo = None
+        self._graphs = {}
 
     # ------------------------------------------------------------------------------------------ query path
     def _encode(self, batch) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -222,7 +253,7 @@ class RetrievalBank:
     def search_embeddings(self, image_half: torch.Tensor, text_half: Optional[torch.Tensor] = None, kk: Optional[int] = None
                           ) -> Dict[str, torch.Tensor]:
         """Query halves (device tensors) -> global top-(k+skip): ``score`` fp32 / ``idx`` int32 ``[B, kk]`` and
-        ``q_sqnorm`` fp32 ``[B]``.  Kernel 1 (queries) -> kernel 2 (+4) -> [all-gather -> kernel 4]."""
+        ``q_bias`` fp32 ``[B]`` (= -0.5*|q|^2).  Kernel 1 (queries) -> kernel 2 (+4) -> [all-gather -> kernel 4]."""
         if kk is None:
             kk = self.retrieval_k + (1 if self.is_training_phase else 0)
         q, qbias = K.bank_build(image_half, text_half, normalise=self.normalise)
@@ -240,7 +271,21 @@ class RetrievalBank:
             idx = torch.full((b, kk), -1, dtype=torch.int32, device=self.device)
         if self.exchange.world_size > 1:
             keys, score, idx = K.merge_topk(self.exchange.gather(keys))
-        return {"keys": keys, "score": score, "idx": idx, "q_sqnorm": qbias * -2.0}
+        return {"keys": keys, "score": score, "idx": idx, "q_bias": qbias}      # |q|^2 = -2 * q_bias
+
+    def _graphed_search(self, img: torch.Tensor, txt: Optional[torch.Tensor], kk: int) -> Dict[str, torch.Tensor]:
+        """The search chain (kernel 1 -> 2 -> 4 -> [all-gather -> 4]) captured once per shape in a CUDA graph and
+        replayed: at small shards the chain is launch-latency-bound.  Every rank of a sharded job must
+        take this path for the same shapes (the NCCL all-gather is part of the graph)."""
+        key = (tuple(img.shape), img.dtype, None if txt is None else tuple(txt.shape), kk)
+        g = self._graphs.get(key)
+        if g is None:
+            g = _SearchGraph(self, img, txt, kk)
+            self._graphs[key] = g
+        res = g.run(img, txt)
+        if self.memoise:       # the graph's outputs are static buffers; a memoised result must survive the next call
+            res = {k_: v.clone() for k_, v in res.items()}
+        return res
 
     def _lut(self, k: int) -> torch.Tensor:
         t = self._lut_cache.get(k)
@@ -268,7 +313,8 @@ class RetrievalBank:
         k = self.retrieval_k
         with torch.no_grad():
             img, txt = self._encode(batch)
-        res = self.search_embeddings(img, txt, kk=k + skip)
+        res = self._graphed_search(img, txt, k + skip) if self.use_cuda_graph else \
+            self.search_embeddings(img, txt, kk=k + skip)
         out = {"skip": skip, "k": k, "device": res}       # everything stays on the device until somebody asks
         if self.memoise:
             try:
@@ -284,7 +330,7 @@ class RetrievalBank:
             res = r["device"]
             r["idx"] = res["idx"].cpu().numpy()
             r["score"] = res["score"].cpu().numpy()
-            r["q_sqnorm"] = res["q_sqnorm"].cpu().numpy()
+            r["q_sqnorm"] = res["q_bias"].cpu().numpy() * -2.0
         return r
 
     def retrieve_closest_qa_pairs(self, batch, return_ans: bool = False, return_info=None, return_dists: bool = False,

@@ -28,6 +28,7 @@ struct mpr_context {
     PFN_encodeTiled encode = nullptr;
     std::vector<cudaEvent_t> prof_events;   // start/stop pairs, used only between mpr_profile_begin/end
     int prof_used = -1;                     // -1 = profiling off
+    int prof_last_n = 0;                    // launches recorded by the last begin/end pair
     char err[512] = {0};
 };
 
@@ -223,6 +224,13 @@ int mpr_profile_end(mpr_handle_t h, float* total_ms, int* n_launches) {
     }
     *total_ms = total;
     *n_launches = n;
+    h->prof_last_n = n;
+    return MPR_OK;
+}
+
+int mpr_profile_launch_ms(mpr_handle_t h, int i, float* ms) {
+    if (!h || !ms || i < 0 || i >= h->prof_last_n) return fail(h, MPR_EINVAL, "bad launch index");
+    CUDA_TRY(h, cudaEventElapsedTime(ms, h->prof_events[2 * i], h->prof_events[2 * i + 1]));
     return MPR_OK;
 }
 
@@ -305,7 +313,8 @@ int mpr_search_topk(mpr_handle_t h, const uint16_t* q, int b, const uint16_t* ba
     if (rc) return rc;
     const int warps_per_block = 4;
     merge_topk_kernel<<<(b + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(
-        part, pl.n_splits, static_cast<long long>(b) * kk, b, kk, out_keys, out_score, out_idx);
+        part, pl.n_splits, 1ll, static_cast<long long>(kk) * pl.n_splits, static_cast<long long>(pl.n_splits), b, kk,
+        out_keys, out_score, out_idx);
     CUDA_TRY(h, cudaGetLastError());
     return MPR_OK;
 }
@@ -318,8 +327,9 @@ int mpr_merge_topk(mpr_handle_t h, const uint64_t* in_keys, int n_lists, int b, 
     if (kk < 1 || kk > MPR_MAX_KK) return fail(h, MPR_EINVAL, "k + skip must be in [1, %d] (got %d)", MPR_MAX_KK, kk);
     const int warps_per_block = 4;
     merge_topk_kernel<<<(b + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0,
-                        static_cast<cudaStream_t>(stream)>>>(in_keys, n_lists, static_cast<long long>(b) * kk, b, kk,
-                                                             out_keys, out_score, out_idx);
+                        static_cast<cudaStream_t>(stream)>>>(in_keys, n_lists, static_cast<long long>(b) * kk,
+                                                             static_cast<long long>(kk), 1ll, b, kk, out_keys,
+                                                             out_score, out_idx);
     CUDA_TRY(h, cudaGetLastError());
     return MPR_OK;
 }

@@ -54,7 +54,7 @@ struct ScanParams {
     uint32_t idx_base; // global row index of this shard's row 0
     uint64_t bank_policy;
     const float* bias;     // [n_local]
-    uint64_t* part_keys;   // [n_splits][b_total][kk]
+    uint64_t* part_keys;   // [b_total][kk][n_splits]
     float* dump;           // debug: [b_total][n_local] scores, or nullptr
     int* err;              // device word that receives the code of a starved barrier
 };
@@ -304,12 +304,13 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             if (lane == 0) ptx::mbar_arrive(bar_tempty(buf));
         }
 
-        // partial result of this (split, q-tile): part_keys[split][q0 + row][0..kk)
+        // partial result of this (split, q-tile): part_keys[q0 + row][rank][split] — rank-major per query, so the
+        // merge kernel's walk over all splits' rank-i candidates is one contiguous stream
         if (warp_has_work) {
             flush();
             if (valid) {
-                uint64_t* dst = p.part_keys + (static_cast<size_t>(split) * p.b_total + q0 + row) * kk;
-                for (int i = 0; i < kk; ++i) dst[i] = my_list[i];
+                uint64_t* dst = p.part_keys + static_cast<size_t>(q0 + row) * kk * p.n_splits + split;
+                for (int i = 0; i < kk; ++i) dst[static_cast<size_t>(i) * p.n_splits] = my_list[i];
             }
         }
     }

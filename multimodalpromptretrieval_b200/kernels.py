@@ -179,3 +179,14 @@ def profile_end(device: Optional[int] = None) -> Tuple[float, int]:
     ms, n = C.c_float(0), C.c_int(0)
     h.check(h.lib.mpr_profile_end(h.ptr, C.byref(ms), C.byref(n)), "mpr_profile_end")
     return ms.value, n.value
+
+
+def profile_launches(n: int, device: Optional[int] = None) -> list:
+    """Per-launch scan-kernel times (ms) of the last profile_begin/profile_end pair."""
+    h = handle(device)
+    out = []
+    for i in range(n):
+        ms = C.c_float(0)
+        h.check(h.lib.mpr_profile_launch_ms(h.ptr, i, C.byref(ms)), "mpr_profile_launch_ms")
+        out.append(ms.value)
+    return out

@@ -384,3 +384,25 @@ def test_create_retrieval_dataset_cache_and_additional_data(tmp_path, golden_cas
         base.combined(), base.answers, base.info, extra.combined(), extra.answers, extra.info)
     expect = O.retrieve_closest_qa_pairs(full[qrows], O.bf16_round(oracle_emb), oracle_ans, oracle_info, 5, False)
     assert b2.retrieve_closest_qa_pairs(batch) == expect
+
+
+def test_cuda_graph_path_matches_eager_and_golden(golden_cases, tokenizer):
+    """The captured search chain (RetrievalBank(use_cuda_graph=True)) returns what the eager launches return, across
+    repeated replays with different query batches."""
+    g = golden_cases["k5_train"]
+    eager, batch = _bank_from_golden(g, tokenizer)
+    graphed, _ = _bank_from_golden(g, tokenizer, use_cuda_graph=True)
+    for rep in range(3):
+        b2 = dict(batch)
+        b2["image"] = torch.roll(g.q_img, rep, 0).clone()
+        b2["question"] = g.questions[-rep:] + g.questions[:-rep] if rep else list(g.questions)
+        b2["task"] = g.tasks[-rep:] + g.tasks[:-rep] if rep else list(g.tasks)
+        re_, rg = eager._host(eager._retrieve(b2)), graphed._host(graphed._retrieve(b2))
+        assert np.array_equal(re_["idx"], rg["idx"]) and np.array_equal(re_["score"], rg["score"])
+        ids_e, mask_e = eager.retrieve_prompt_ids(b2)
+        ids_g, mask_g = graphed.retrieve_prompt_ids(b2)
+        assert torch.equal(ids_e, ids_g) and torch.equal(mask_e, mask_g)
+        if rep == 0:
+            assert graphed.retrieve_closest_qa_pairs(b2) == g.j["prompts_quant"]
+            assert np.array_equal(ids_g.cpu().numpy(), g.z["input_ids_quant"])
+    assert len(graphed._graphs) == 1
