@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--k", type=int, default=TOPK)
     ap.add_argument("--dim", type=int, default=DIM)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--max-seconds", type=float, default=420.0, help="watchdog: hard-exit after this many seconds")
     ap.add_argument("--no-graph", action="store_true", help="launch the chain kernel by kernel instead of replaying a CUDA graph")
     return ap.parse_args()
 
@@ -362,13 +363,26 @@ def run_native(args):
         if n_gpus == 1 and not args.no_cpu_baseline:
             result["cpu_baseline"] = cpu_baseline(args)
         print(json.dumps(result), flush=True)
+    # Teardown: CUDA graphs that captured NCCL kernels must go before the communicator does, and a hung
+    # communicator teardown must never keep the launcher alive — leave through os._exit once every rank is done.
+    sys.stdout.flush()
+    if not args.no_graph:
+        graph_out.clear()
+        graph.reset()
+    bank._graphs.clear()
+    torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+    os._exit(0)
 
 
 def main():
     args = parse_args()
+    # hard stop: a benchmark must not hang a GPU box (or the driver's scaling run) under any circumstances
+    watchdog = threading.Timer(args.max_seconds, lambda: (sys.stderr.write("bench watchdog expired\n"), os._exit(124)))
+    watchdog.daemon = True
+    watchdog.start()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
