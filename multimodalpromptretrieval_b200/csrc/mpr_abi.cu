@@ -55,7 +55,7 @@ static inline int pow2_ceil(int v) { int p = 1; while (p < v) p <<= 1; return p;
 
 // ------------------------------------------------------------------------------------------------ planning
 struct ScanPlan {
-    int n_chunks, q_tile, q_box_rows, n_qtiles, n_splits, n_tiles, n_stages, kk_pad;
+    int n_chunks, q_tile, q_box_rows, n_qtiles, n_splits, n_tiles, n_stages, kk_pad, cand_cap;
     uint32_t smem_bytes;
 };
 
@@ -71,6 +71,9 @@ static int make_plan(mpr_context* h, int b, int64_t n_local, int d, int kk, Scan
     pl->n_tiles = static_cast<int>((n_local + kTileRows - 1) / kTileRows);
     int q_tile_max = 128;
     while (q_tile_max > 8 && static_cast<long long>(q_tile_max) * d * 2 > 131072) q_tile_max >>= 1;
+    // Shared memory is split between the resident q-tile, the per-query lists and the bank ring.  Reading the bank
+    // twice (two q-tiles) costs far more than a shallower ring, so the q-tile is only halved when fewer than 3 stages
+    // (48 KiB in flight per SM) would remain even with the smallest pending buffers.
     int stages = 0;
     for (;;) {
         if (b <= q_tile_max) {
@@ -82,11 +85,13 @@ static int make_plan(mpr_context* h, int b, int64_t n_local, int d, int kk, Scan
             pl->n_qtiles = (b + q_tile_max - 1) / q_tile_max;
             pl->q_box_rows = q_tile_max;
         }
-        const ScanSmemLayout fixed = scan_smem_layout(pl->n_chunks, pl->q_box_rows, pl->kk_pad, 0);
-        const int avail = kMaxSmem - 1024 - static_cast<int>(fixed.total);
-        stages = avail / kStageBytes;
-        // the resident q-tile competes with the bank ring for shared memory: keep at least 4 stages (64 KiB) in flight
-        if (stages >= 4 || q_tile_max <= 32 || pl->q_box_rows < q_tile_max) break;
+        for (pl->cand_cap = kCandCapMax; pl->cand_cap >= 10; pl->cand_cap -= 2) {
+            const ScanSmemLayout fixed = scan_smem_layout(pl->n_chunks, pl->q_box_rows, pl->kk_pad, pl->cand_cap, 0);
+            stages = (kMaxSmem - 1024 - static_cast<int>(fixed.total)) / kStageBytes;
+            if (stages >= 3) break;
+        }
+        if (pl->cand_cap < 10) pl->cand_cap = 10;
+        if (stages >= 3 || q_tile_max <= 32 || pl->q_box_rows < q_tile_max) break;
         q_tile_max >>= 1;
     }
     if (stages > kMaxStages) stages = kMaxStages;
@@ -97,7 +102,7 @@ static int make_plan(mpr_context* h, int b, int64_t n_local, int d, int kk, Scan
     pl->n_splits = h->num_sms / g;
     if (pl->n_splits > pl->n_tiles) pl->n_splits = pl->n_tiles;
     if (pl->n_splits < 1) pl->n_splits = 1;
-    pl->smem_bytes = scan_smem_layout(pl->n_chunks, pl->q_box_rows, pl->kk_pad, stages).total + 1024u;
+    pl->smem_bytes = scan_smem_layout(pl->n_chunks, pl->q_box_rows, pl->kk_pad, pl->cand_cap, stages).total + 1024u;
     return MPR_OK;
 }
 
@@ -132,6 +137,7 @@ static int launch_scan(mpr_context* h, const ScanPlan& pl, const uint16_t* q, in
     p.n_chunks = pl.n_chunks;
     p.kk = kk;
     p.kk_pad = pl.kk_pad;
+    p.cand_cap = pl.cand_cap;
     p.q_tile = pl.q_tile;
     p.q_box_rows = pl.q_box_rows;
     p.n_qtiles = pl.n_qtiles;

@@ -37,7 +37,7 @@ constexpr int kScanThreads = 192;
 constexpr int kMaxStages = 12;
 constexpr int kMaxSmem = 232448;              // 227 KiB opt-in limit per CTA on sm_100
 constexpr int kMaxKK = 32;
-constexpr int kCandCap = 16;                  // per-query candidate buffer (flushed when more than 8 are pending)
+constexpr int kCandCapMax = 16;               // per-query pending-candidate slots (a flush leaves >= 8 free)
 
 struct ScanParams {
     int b_total;       // queries in the batch
@@ -45,6 +45,7 @@ struct ScanParams {
     int n_chunks;      // D / 64
     int kk;            // list length (k + skip), 1..32
     int kk_pad;        // next power of two >= kk
+    int cand_cap;      // pending-candidate slots per query (9..16)
     int q_tile;        // queries per q-tile
     int q_box_rows;    // rows of the Q TMA box (multiple of 8, >= valid rows of any q-tile)
     int n_qtiles;
@@ -63,16 +64,19 @@ struct ScanSmemLayout {
     uint32_t q_off, stage_off, list_off, bias_off, bar_off, total;
 };
 
-// Per-query shared-memory row: [kk_pad sorted keys | kCandCap pending candidates | 1 pad]; the odd stride (in
+// Per-query shared-memory row: [kk_pad sorted keys | cand_cap pending candidates | pad]; the odd stride (in
 // 8-byte words) keeps the 32 lanes of a warp, each walking its own row, on distinct banks.
-__host__ __device__ inline uint32_t scan_row_stride(int kk_pad) { return static_cast<uint32_t>(kk_pad) + kCandCap + 1u; }
+__host__ __device__ inline uint32_t scan_row_stride(int kk_pad, int cand_cap) {
+    return (static_cast<uint32_t>(kk_pad) + cand_cap) | 1u;
+}
 
-__host__ __device__ inline ScanSmemLayout scan_smem_layout(int n_chunks, int q_box_rows, int kk_pad, int n_stages) {
+__host__ __device__ inline ScanSmemLayout scan_smem_layout(int n_chunks, int q_box_rows, int kk_pad, int cand_cap,
+                                                           int n_stages) {
     ScanSmemLayout l;
     l.q_off = 0;
     l.stage_off = static_cast<uint32_t>(n_chunks) * q_box_rows * 128u;          // multiple of 1024
     l.list_off = l.stage_off + static_cast<uint32_t>(n_stages) * kStageBytes;
-    l.bias_off = l.list_off + static_cast<uint32_t>(kUmmaM) * scan_row_stride(kk_pad) * 8u;
+    l.bias_off = l.list_off + static_cast<uint32_t>(kUmmaM) * scan_row_stride(kk_pad, cand_cap) * 8u;
     l.bar_off = l.bias_off + kAccBufs * kTileRows * 4u;
     l.total = l.bar_off + (1 + 2 * kMaxStages + 2 * kAccBufs) * 8u + 16u;
     return l;
@@ -90,7 +94,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const uint32_t base = (raw_addr + 1023u) & ~1023u;   // SWIZZLE_128B atoms need 1024-byte alignment
     uint8_t* smem = smem_raw + (base - raw_addr);
 
-    const ScanSmemLayout lay = scan_smem_layout(p.n_chunks, p.q_box_rows, p.kk_pad, p.n_stages);
+    const ScanSmemLayout lay = scan_smem_layout(p.n_chunks, p.q_box_rows, p.kk_pad, p.cand_cap, p.n_stages);
     const uint32_t q_smem = base + lay.q_off;
     const uint32_t stage_smem = base + lay.stage_off;
     uint64_t* lists = reinterpret_cast<uint64_t*>(smem + lay.list_off);
@@ -206,25 +210,29 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         const int ep_tid = (warp - 2) * 32 + lane;     // 0..127, used to stage the bias tile
         const int kk = p.kk;
         const int kk_pad = p.kk_pad;
-        uint64_t* my_list = lists + static_cast<size_t>(row) * scan_row_stride(kk_pad);   // [0, kk) sorted keys
+        uint64_t* my_list = lists + static_cast<size_t>(row) * scan_row_stride(kk_pad, p.cand_cap);   // [0, kk) sorted keys
         uint2* my_pend = reinterpret_cast<uint2*>(my_list + kk_pad);                      // (score bits, row)
         for (int i = 0; i < kk; ++i) my_list[i] = 0ull;
         float thr = valid ? -CUDART_INF_F : CUDART_INF_F;
         int n_pend = 0;
+        const int flush_at = p.cand_cap - 8;           // the next group of 8 scores must always fit
 
         auto flush = [&]() {
             for (int c = 0; c < n_pend; ++c) {
                 const uint2 cand = my_pend[c];
                 const uint64_t key = make_key(__uint_as_float(cand.x), cand.y);
-                if (key > my_list[kk - 1]) {
-                    int j = kk - 1;
-                    while (j > 0) {
-                        const uint64_t above = my_list[j - 1];
-                        if (above >= key) break;
-                        my_list[j] = above;
-                        --j;
+                uint64_t lower = my_list[kk - 1];
+                if (key > lower) {
+                    // Branch-free single pass from the bottom: new[j] = old[j-1] >= key ? max(old[j], key) : old[j-1].
+                    // No iteration depends on a loaded value for control flow, so the LDS/STS stream pipelines
+                    // (a compare-and-break insertion loop pays one shared-memory latency per shifted element).
+#pragma unroll 4
+                    for (int j = kk - 1; j > 0; --j) {
+                        const uint64_t upper = my_list[j - 1];
+                        my_list[j] = upper >= key ? (lower > key ? lower : key) : upper;
+                        lower = upper;
                     }
-                    my_list[j] = key;
+                    my_list[0] = lower > key ? lower : key;
                 }
             }
             n_pend = 0;
@@ -294,7 +302,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                                     ++n_pend;
                                 }
                             }
-                            if (__any_sync(kFullMask, n_pend > kCandCap - 8)) flush();
+                            if (__any_sync(kFullMask, n_pend > flush_at)) flush();
                         }
                     }
                 }

@@ -19,6 +19,8 @@ can overlap the bank scan).  Everything else is gathered on the device from tabl
 """
 from __future__ import annotations
 
+import itertools
+import os
 from typing import List, Sequence, Tuple
 
 import numpy as np
@@ -62,18 +64,42 @@ def prefix_texts(tasks: Sequence[str], questions: Sequence[str], use_quantifier:
 
 def _csr(rows: Sequence[Sequence[int]]) -> Tuple[np.ndarray, np.ndarray]:
     off = np.zeros(len(rows) + 1, dtype=np.int32)
-    np.cumsum([len(r) for r in rows], out=off[1:])
-    ids = np.fromiter((t for r in rows for t in r), dtype=np.int32, count=int(off[-1]))
+    np.cumsum(list(map(len, rows)), out=off[1:])
+    ids = np.fromiter(itertools.chain.from_iterable(rows), dtype=np.int32, count=int(off[-1]))
     return ids, off
 
 
+def _fast_encoder(tokenizer):
+    """Batch encoder ``list[str] -> list[list[int]]`` without special tokens.  HF's ``__call__`` costs ~70 us per
+    string; when the tokenizer is backed by a sentencepiece file the processor is used directly (C++ batch call), but
+    only after it reproduced the HF tokenizer's output on a probe set — otherwise the HF call is kept."""
+    def hf(texts):
+        return tokenizer(list(texts), add_special_tokens=False)["input_ids"]
+
+    vocab_file = getattr(tokenizer, "vocab_file", None)
+    if not vocab_file or not os.path.exists(vocab_file):
+        return hf
+    try:
+        import sentencepiece as spm
+        sp = spm.SentencePieceProcessor(model_file=vocab_file)
+        probe = ["Answer the Modality question:", "what modality is used to take this image?I", "lung?The", "",
+                 "very likely", "x-ray, mri", "  two  spaces ", "Mixed Case: 12 3?", TAIL_QUANT, TAIL_PLAIN]
+        if sp.encode(probe) == hf(probe):
+            return lambda texts: sp.encode(list(texts))
+    except Exception:
+        pass
+    return hf
+
+
 class PromptTables:
-    """Device-resident CSR of the constant segments, the six buckets and every distinct answer of the bank."""
+    """Device-resident CSR of the constant segments, the six buckets and every distinct answer of the bank, plus the
+    host-side tokenisation of the per-query prefixes."""
 
     def __init__(self, tokenizer, answer_strings: Sequence[str], device: torch.device):
         self.tokenizer = tokenizer
         self.pad_id = int(tokenizer.pad_token_id)
         self.eos_id = int(tokenizer.eos_token_id)
+        self.encode = _fast_encoder(tokenizer)
         segs = segment_strings(answer_strings)
         enc = tokenizer(segs, add_special_tokens=False)["input_ids"] if segs else []
         ids, off = _csr(enc)
@@ -82,6 +108,9 @@ class PromptTables:
         self.seg_ids = torch.from_numpy(ids if ids.size else np.zeros(1, np.int32)).to(device)
         self.seg_off = torch.from_numpy(off).to(device)
         self.device = device
+        self._task_head = {}            # task -> tokens("Answer the {task} question:")
+        self._stage = None              # pinned host staging + device buffers for the prefix CSR (grown on demand)
+        self._stage_done = None
 
     def tail_bound(self, use_quantifier: bool) -> int:
         """Upper bound on tokens appended after the prefix (const + bucket + answer + </s>)."""
@@ -90,14 +119,38 @@ class PromptTables:
                 self.max_answer_len + 1
         return int(self.seg_lens[SEG_PLAIN]) + self.max_answer_len + 1
 
+    def prefix_tokens(self, tasks: Sequence[str], questions: Sequence[str], use_quantifier: bool
+                      ) -> Tuple[np.ndarray, np.ndarray]:
+        """Host CSR of tokens("Answer the {task} question: " + question + "I"|"The").  The task part ends at a
+        whitespace boundary, so it is tokenised once per distinct task and concatenated with tokens(question + head)."""
+        head = HEAD_QUANT if use_quantifier else HEAD_PLAIN
+        missing = [t for t in set(tasks) if t not in self._task_head]
+        if missing:
+            for t, ids in zip(missing, self.encode([f"Answer the {t} question:" for t in missing])):
+                self._task_head[t] = list(ids)
+        tails = self.encode([q + head for q in questions])
+        return _csr([self._task_head[t] + list(tail) for t, tail in zip(tasks, tails)])
+
     def prefixes(self, tasks: Sequence[str], questions: Sequence[str], use_quantifier: bool
                  ) -> Tuple[torch.Tensor, torch.Tensor, int]:
-        """tokens("Answer the {task} question: " + question + "I"|"The") per query as a device CSR, plus the
-        longest prefix length."""
-        texts = prefix_texts(tasks, questions, use_quantifier)
-        enc = self.tokenizer(texts, add_special_tokens=False)["input_ids"]
-        ids, off = _csr(enc)
-        longest = int(np.diff(off).max()) if len(texts) else 0
-        ids_t = torch.from_numpy(ids if ids.size else np.zeros(1, np.int32)).pin_memory().to(self.device, non_blocking=True)
-        off_t = torch.from_numpy(off).pin_memory().to(self.device, non_blocking=True)
-        return ids_t, off_t, longest
+        """:meth:`prefix_tokens` staged through pinned memory onto the device; also returns the longest prefix."""
+        ids, off = self.prefix_tokens(tasks, questions, use_quantifier)
+        n_ids, n_off = max(int(ids.size), 1), int(off.size)
+        longest = int(np.diff(off).max()) if len(tasks) else 0
+        if self._stage is None or self._stage[0].numel() < n_ids or self._stage[1].numel() < n_off:
+            cap_ids, cap_off = max(2 * n_ids, 4096), max(2 * n_off, 512)
+            self._stage = (torch.empty(cap_ids, dtype=torch.int32).pin_memory(),
+                           torch.empty(cap_off, dtype=torch.int32).pin_memory(),
+                           torch.empty(cap_ids, dtype=torch.int32, device=self.device),
+                           torch.empty(cap_off, dtype=torch.int32, device=self.device))
+            self._stage_done = None
+        if self._stage_done is not None:
+            self._stage_done.synchronize()          # the previous H2D out of the pinned buffers has finished
+        h_ids, h_off, d_ids, d_off = self._stage
+        h_ids[:ids.size].copy_(torch.from_numpy(ids))
+        h_off[:n_off].copy_(torch.from_numpy(off))
+        d_ids[:n_ids].copy_(h_ids[:n_ids], non_blocking=True)
+        d_off[:n_off].copy_(h_off[:n_off], non_blocking=True)
+        self._stage_done = torch.cuda.Event()
+        self._stage_done.record()
+        return d_ids[:n_ids], d_off[:n_off], longest

@@ -118,3 +118,17 @@ def test_no_fallback_without_gpu():
     lib = _native.load()
     h = ctypes.c_void_p()
     assert lib.mpr_create(0, ctypes.byref(h)) != 0 and not h.value
+
+
+def test_fast_prefix_tokenisation_equals_hf_tokenizer(tokenizer):
+    """prefix = cached tokens("Answer the {task} question:") + tokens(question + "I"|"The") through the direct
+    sentencepiece batch call == the HF tokenizer on the whole prefix string (incl. empty / space-padded questions)."""
+    from multimodalpromptretrieval_b200 import synthetic as S
+    tables = prompt.PromptTables(tokenizer, ["yes", "no", "left lung"], torch.device("cpu"))
+    questions = [f"{q} #{i}" for i, q in enumerate(S.make_questions(64, 11))] + ["", " lead", "trail ", "a  b"]
+    tasks = [S.TASKS[i % len(S.TASKS)] for i in range(len(questions))]
+    for quant in (True, False):
+        ids, off = tables.prefix_tokens(tasks, questions, quant)
+        ref = tokenizer(prompt.prefix_texts(tasks, questions, quant), add_special_tokens=False)["input_ids"]
+        assert [ids[off[i]:off[i + 1]].tolist() for i in range(len(questions))] == ref
+    assert tables.tail_bound(True) > tables.tail_bound(False) - 8 and tables.max_answer_len >= 1
