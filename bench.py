@@ -52,6 +52,8 @@ def parse_args():
     ap.add_argument("--dim", type=int, default=DIM)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--max-seconds", type=float, default=420.0, help="watchdog: hard-exit after this many seconds")
+    ap.add_argument("--exchange", default="nccl", choices=["nccl", "p2p"],
+                    help="multi-GPU candidate exchange: NCCL all-gather + merge, or peer-memory push + flag wait")
     ap.add_argument("--no-graph", action="store_true", help="launch the chain kernel by kernel instead of replaying a CUDA graph")
     return ap.parse_args()
 
@@ -208,7 +210,7 @@ def run_native(args):
 
     tokenizer = S.load_tokenizer(os.path.join(ROOT, "tests", "golden", "spm"))
     bank = RetrievalBank(clip_model=PassThroughClip(), clip_tokenize=None, tokenizer=tokenizer, device=dev,
-                         memoise=False, use_cuda_graph=not args.no_graph)
+                         memoise=False, use_cuda_graph=not args.no_graph, exchange=args.exchange)
     bank.clip_tokenize = lambda qs: None
 
     # ---- synthetic bank: chunk c is seeded by c, so the bank's contents do not depend on the GPU count
@@ -366,6 +368,7 @@ def run_native(args):
             "gpu_launches_per_step": launches_per_step,
             "roofline": roofline,
             "plan": K.search_plan(b, n_local, d, kk, dev.index), "cuda_graph": not args.no_graph,
+            "exchange": args.exchange if world > 1 else None,
             "sample_output": {"prompt_tokens": int(out0["length"].max().item()),
                               "majority_answer0": S.ROCO_ANSWERS[int(out0["majority_answer"][0].item())]},
         }

@@ -85,6 +85,22 @@ int mpr_merge_topk(mpr_handle_t h, const uint64_t* in_keys, int n_lists, int b, 
                    float* out_score, int32_t* out_idx, void* stream);
 
 /*
+ * Candidate exchange over NVLink peer memory (alternative to NCCL all-gather + mpr_merge_topk on one NVSwitch box;
+ * csrc/exchange.cuh).  Every rank allocates one buffer of mpr_exchange_bytes(world, cap) bytes that is mapped into all
+ * peers (symmetric memory), zero-filled before first use.  peer_bufs is a HOST array of `world` device pointers, entry r
+ * = rank r's buffer as addressable from this device (entry `rank` = the local buffer).  cap >= b*kk.
+ *   mpr_exchange_push : store this rank's [b][kk] keys into every rank's buffer and raise the delivery flags.
+ *   mpr_exchange_merge: wait for all `world` deliveries, merge them (score desc, row asc) into the global top-kk.
+ * Both are single launches on `stream`, keep their epoch in device memory and are CUDA-graph capturable.  New in the
+ * build: the reference is single-device (main.py:58-61).
+ */
+size_t mpr_exchange_bytes(int world, int cap);
+int mpr_exchange_push(mpr_handle_t h, const uint64_t* local_keys, int b, int kk, int rank, int world,
+                      void* const* peer_bufs, int cap, void* stream);
+int mpr_exchange_merge(mpr_handle_t h, void* my_buf, int world, int cap, int b, int kk, uint64_t* out_keys,
+                       float* out_score, int32_t* out_idx, void* stream);
+
+/*
  * Kernel 3 — retrieved rows -> answers -> majority vote -> quantifier bucket -> prompt token ids.
  * Replaces: dataset/VQAFeatureDataset.py:199,215-230 and the tokenizer call of
  *           architectures/T5VisionModel.py:153-167 (padding="longest", truncation to max_len, </s> appended).

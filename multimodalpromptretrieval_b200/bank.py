@@ -24,7 +24,7 @@ import torch
 
 from . import kernels as K
 from .prompt import PromptTables, bucket_lut, prompt_string
-from .sharding import CandidateExchange, shard_bounds
+from .sharding import CandidateExchange, P2PExchange, shard_bounds
 
 _INFO_KEYS = ("question_type", "question_id", "question")
 
@@ -83,7 +83,7 @@ class RetrievalBank:
                  process_group=None, shard: bool = True, max_source_length: int = 512, name: str = "VQADataset",
                  cache_root: str = "cache", additional_root: str = os.path.join("synthetic_data", "cache",
                                                                                "ROCOFeatureDataset"),
-                 memoise: bool = True, use_cuda_graph: bool = False):
+                 memoise: bool = True, use_cuda_graph: bool = False, exchange: str = "nccl"):
         if not torch.cuda.is_available():
             raise RuntimeError("RetrievalBank needs a B200 (sm_100a) GPU; there is no CPU fallback path")
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
@@ -97,6 +97,11 @@ class RetrievalBank:
         self.additional_root = additional_root
         self.memoise = memoise
         self.use_cuda_graph = bool(use_cuda_graph)
+        if exchange not in ("nccl", "p2p"):
+            raise ValueError("exchange must be 'nccl' (all-gather + merge) or 'p2p' (peer-memory push + flag wait)")
+        self.exchange_mode = exchange
+        self._p2p: Optional[P2PExchange] = None
+        self._process_group = process_group if shard else None
         self._graphs: Dict[tuple, "_SearchGraph"] = {}
         self.exchange = CandidateExchange(process_group if shard else None)
         if not shard:
@@ -270,7 +275,12 @@ class RetrievalBank:
             score = torch.full((b, kk), float("-inf"), device=self.device)
             idx = torch.full((b, kk), -1, dtype=torch.int32, device=self.device)
         if self.exchange.world_size > 1:
-            keys, score, idx = K.merge_topk(self.exchange.gather(keys))
+            if self.exchange_mode == "p2p":
+                if self._p2p is None or self._p2p.cap < b * kk:
+                    self._p2p = P2PExchange(self.device, max(b * kk, 4096), self._process_group)
+                keys, score, idx = self._p2p.exchange(keys)
+            else:
+                keys, score, idx = K.merge_topk(self.exchange.gather(keys))
         return {"keys": keys, "score": score, "idx": idx, "q_bias": qbias}      # |q|^2 = -2 * q_bias
 
     def _graphed_search(self, img: torch.Tensor, txt: Optional[torch.Tensor], kk: int) -> Dict[str, torch.Tensor]:

@@ -11,6 +11,7 @@
 
 #include "../../include/mpr_b200.h"
 #include "bank_build.cuh"
+#include "exchange.cuh"
 #include "merge_topk.cuh"
 #include "prompt_gather.cuh"
 #include "scan_topk.cuh"
@@ -336,6 +337,43 @@ int mpr_merge_topk(mpr_handle_t h, const uint64_t* in_keys, int n_lists, int b, 
                         static_cast<cudaStream_t>(stream)>>>(in_keys, n_lists, static_cast<long long>(b) * kk,
                                                              static_cast<long long>(kk), 1ll, b, kk, out_keys,
                                                              out_score, out_idx);
+    CUDA_TRY(h, cudaGetLastError());
+    return MPR_OK;
+}
+
+size_t mpr_exchange_bytes(int world, int cap) {
+    if (world < 1 || world > kXchgMaxWorld || cap < 1) return 0;
+    return xchg_bytes(world, cap);
+}
+
+int mpr_exchange_push(mpr_handle_t h, const uint64_t* local_keys, int b, int kk, int rank, int world,
+                      void* const* peer_bufs, int cap, void* stream) {
+    if (!h) return fail(nullptr, MPR_EINVAL, "null handle");
+    if (!local_keys || !peer_bufs) return fail(h, MPR_EINVAL, "null pointer");
+    if (world < 1 || world > kXchgMaxWorld || rank < 0 || rank >= world)
+        return fail(h, MPR_EINVAL, "bad rank/world %d/%d (max world %d)", rank, world, kXchgMaxWorld);
+    if (b < 1 || kk < 1 || kk > MPR_MAX_KK || static_cast<long long>(b) * kk > cap)
+        return fail(h, MPR_EINVAL, "b*kk = %lld exceeds the exchange capacity %d", static_cast<long long>(b) * kk, cap);
+    XchgPeers peers;
+    for (int r = 0; r < kXchgMaxWorld; ++r) peers.buf[r] = r < world ? static_cast<unsigned char*>(peer_bufs[r]) : nullptr;
+    for (int r = 0; r < world; ++r)
+        if (!peers.buf[r] || !aligned16(peers.buf[r])) return fail(h, MPR_EINVAL, "peer buffer %d is null or unaligned", r);
+    xchg_push_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(local_keys, b * kk, rank, world, cap, peers);
+    CUDA_TRY(h, cudaGetLastError());
+    return MPR_OK;
+}
+
+int mpr_exchange_merge(mpr_handle_t h, void* my_buf, int world, int cap, int b, int kk, uint64_t* out_keys,
+                       float* out_score, int32_t* out_idx, void* stream) {
+    if (!h) return fail(nullptr, MPR_EINVAL, "null handle");
+    if (!my_buf || !aligned16(my_buf)) return fail(h, MPR_EINVAL, "exchange buffer is null or unaligned");
+    if (world < 1 || world > kXchgMaxWorld) return fail(h, MPR_EINVAL, "bad world %d", world);
+    if (b < 1 || kk < 1 || kk > MPR_MAX_KK || static_cast<long long>(b) * kk > cap)
+        return fail(h, MPR_EINVAL, "b*kk = %lld exceeds the exchange capacity %d", static_cast<long long>(b) * kk, cap);
+    const int warps_per_block = 4;
+    xchg_merge_kernel<<<(b + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0,
+                        static_cast<cudaStream_t>(stream)>>>(static_cast<unsigned char*>(my_buf), world, cap, b, kk,
+                                                             out_keys, out_score, out_idx, h->d_err);
     CUDA_TRY(h, cudaGetLastError());
     return MPR_OK;
 }

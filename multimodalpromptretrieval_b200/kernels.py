@@ -190,3 +190,32 @@ def profile_launches(n: int, device: Optional[int] = None) -> list:
         h.check(h.lib.mpr_profile_launch_ms(h.ptr, i, C.byref(ms)), "mpr_profile_launch_ms")
         out.append(ms.value)
     return out
+
+
+def exchange_bytes(world: int, cap: int) -> int:
+    return int(_native.load().mpr_exchange_bytes(world, cap))
+
+
+def exchange_push(keys: torch.Tensor, rank: int, peer_ptrs, cap: int) -> None:
+    """P2P push of this rank's candidate keys ``[b, kk]`` into every rank's exchange buffer (``peer_ptrs[r]`` = device
+    address of rank r's buffer as mapped on this device)."""
+    h = handle(keys.device.index)
+    assert keys.dtype == torch.int64 and keys.dim() == 2 and keys.is_contiguous()
+    b, kk = keys.shape
+    world = len(peer_ptrs)
+    arr = (C.c_void_p * world)(*[C.c_void_p(int(p)) for p in peer_ptrs])
+    h.check(h.lib.mpr_exchange_push(h.ptr, _ptr(keys), b, kk, rank, world, arr, cap, _stream()), "mpr_exchange_push")
+
+
+def exchange_merge(my_buf: torch.Tensor, world: int, cap: int, b: int, kk: int
+                   ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Wait for all ``world`` deliveries into ``my_buf`` and merge them into the global top-kk."""
+    h = handle(my_buf.device.index)
+    dev = my_buf.device
+    out_keys = torch.empty((b, kk), dtype=torch.int64, device=dev)
+    out_score = torch.empty((b, kk), dtype=torch.float32, device=dev)
+    out_idx = torch.empty((b, kk), dtype=torch.int32, device=dev)
+    rc = h.lib.mpr_exchange_merge(h.ptr, _ptr(my_buf), world, cap, b, kk, _ptr(out_keys), _ptr(out_score),
+                                  _ptr(out_idx), _stream())
+    h.check(rc, "mpr_exchange_merge")
+    return out_keys, out_score, out_idx

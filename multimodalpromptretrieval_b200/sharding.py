@@ -54,3 +54,38 @@ class CandidateExchange:
             self._buf = torch.empty(shape, dtype=torch.int64, device=keys.device)
         dist.all_gather_into_tensor(self._buf, keys, group=self.group)
         return self._buf.view(self.world_size, b, kk)
+
+
+class P2PExchange:
+    """The same exchange without NCCL: every rank stores its candidates straight into every peer's symmetric-memory
+    buffer over NVLink and raises a flag; the merge kernel waits on the flags (csrc/exchange.cuh).  Two launches, no
+    collective library on the data path, epoch kept on the device (CUDA-graph capturable).  With ``world_size == 1`` it
+    degenerates to a self-exchange through an ordinary device buffer (used by the single-GPU tests)."""
+
+    def __init__(self, device: torch.device, cap: int, group: Optional[dist.ProcessGroup] = None):
+        from . import kernels as K
+        self._K = K
+        self.cap = int(cap)
+        if dist.is_available() and dist.is_initialized():
+            self.rank, self.world_size = dist.get_rank(group), dist.get_world_size(group)
+        else:
+            self.rank, self.world_size = 0, 1
+        nbytes = K.exchange_bytes(self.world_size, self.cap)
+        if self.world_size == 1:
+            self.buf = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+            self.peer_ptrs = [self.buf.data_ptr()]
+            self._hdl = None
+        else:
+            import torch.distributed._symmetric_memory as symm_mem
+            self.buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=device)
+            self.buf.zero_()
+            self._hdl = symm_mem.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+            self.peer_ptrs = [int(p) for p in self._hdl.buffer_ptrs]
+            torch.cuda.synchronize(device)
+            dist.barrier(group)                 # nobody pushes before every buffer is zeroed
+
+    def exchange(self, keys: torch.Tensor):
+        b, kk = keys.shape
+        assert b * kk <= self.cap
+        self._K.exchange_push(keys, self.rank, self.peer_ptrs, self.cap)
+        return self._K.exchange_merge(self.buf, self.world_size, self.cap, b, kk)

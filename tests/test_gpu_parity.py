@@ -406,3 +406,34 @@ def test_cuda_graph_path_matches_eager_and_golden(golden_cases, tokenizer):
             assert graphed.retrieve_closest_qa_pairs(b2) == g.j["prompts_quant"]
             assert np.array_equal(ids_g.cpu().numpy(), g.z["input_ids_quant"])
     assert len(graphed._graphs) == 1
+
+
+@pytest.mark.parametrize("world", [1, 2, 8])
+def test_p2p_exchange_protocol_on_one_gpu(K, world):
+    """The peer-memory exchange (csrc/exchange.cuh), with all `world` ranks played by one GPU IN SEQUENCE (every push is
+    launched before any merge, so no kernel ever waits on a kernel that is not already complete): epochs advance,
+    the double-buffered slots do not mix exchanges, and each rank's merge equals the oracle merge of all lists."""
+    b, kk, cap = 37, 6, 512
+    nbytes = K.exchange_bytes(world, cap)
+    assert nbytes == 1024 + 2 * world * cap * 8
+    bufs = [torch.zeros(nbytes, dtype=torch.uint8, device=dev()) for _ in range(world)]
+    ptrs = [t.data_ptr() for t in bufs]
+    rng = np.random.default_rng(world)
+    for step in range(5):                                                   # several epochs, both parities
+        score = rng.standard_normal((world, b, kk)).astype(np.float32)
+        score[:, :, 0] = 0.25                                               # exact score ties across ranks
+        idx = rng.permutation(world * b * kk).reshape(world, b, kk).astype(np.int32)
+        keys = np.sort(O.keys_from(score, idx), axis=2)[:, :, ::-1].copy()
+        keys_d = [torch.from_numpy(keys[r].view(np.int64)).to(dev()) for r in range(world)]
+        for r in range(world):
+            K.exchange_push(keys_d[r], r, ptrs, cap)
+        ref = O.merge_keys(keys, kk)
+        for r in range(world):
+            ok, osc, oi = K.exchange_merge(bufs[r], world, cap, b, kk)
+            assert np.array_equal(ok.cpu().numpy().view(np.uint64), ref), (step, r)
+            assert np.array_equal(oi.cpu().numpy(), O.decode_keys(ref)[1])
+        torch.cuda.synchronize()
+        for r in range(world):
+            ctrl = bufs[r][:8].cpu().numpy().view(np.uint32)
+            assert ctrl[0] == step + 1 and ctrl[1] == 0                    # epoch published, done-counter reset
+    assert K.handle(0).device_error() == 0
