@@ -5,6 +5,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <vector>
@@ -28,6 +29,8 @@ struct mpr_context {
     int* d_err = nullptr;
     PFN_encodeTiled encode = nullptr;
     std::vector<cudaEvent_t> prof_events;   // start/stop pairs, used only between mpr_profile_begin/end
+    int use_q_tmem = 1;                     // q-tile as TMEM A operand when D <= 512 (MPR_NO_QTMEM=1 disables)
+    int use_cluster = 1;                    // CTA-pair TMA multicast in the tensor-bound regime (MPR_NO_CLUSTER=1 disables)
     int prof_used = -1;                     // -1 = profiling off
     int prof_last_n = 0;                    // launches recorded by the last begin/end pair
     char err[512] = {0};
@@ -57,6 +60,7 @@ static inline int pow2_ceil(int v) { int p = 1; while (p < v) p <<= 1; return p;
 // ------------------------------------------------------------------------------------------------ planning
 struct ScanPlan {
     int n_chunks, q_tile, q_box_rows, n_qtiles, n_splits, n_tiles, n_stages, kk_pad, cand_cap;
+    bool q_tmem;       // q-tile in tensor memory (TMEM A operand) instead of shared memory
     uint32_t smem_bytes;
 };
 
@@ -70,8 +74,10 @@ static int make_plan(mpr_context* h, int b, int64_t n_local, int d, int kk, Scan
     pl->n_chunks = d / kChunkK;
     pl->kk_pad = pow2_ceil(kk);
     pl->n_tiles = static_cast<int>((n_local + kTileRows - 1) / kTileRows);
+    // D <= 512: the q-tile (128 x D bf16) fits 256 TMEM columns next to two 128-column accumulators
+    pl->q_tmem = h->use_q_tmem && d <= 512;
     int q_tile_max = 128;
-    while (q_tile_max > 8 && static_cast<long long>(q_tile_max) * d * 2 > 131072) q_tile_max >>= 1;
+    while (!pl->q_tmem && q_tile_max > 8 && static_cast<long long>(q_tile_max) * d * 2 > 131072) q_tile_max >>= 1;
     // Shared memory is split between the resident q-tile, the per-query lists and the bank ring.  Reading the bank
     // twice (two q-tiles) costs far more than a shallower ring, so the q-tile is only halved when fewer than 3 stages
     // (48 KiB in flight per SM) would remain even with the smallest pending buffers.
@@ -86,13 +92,14 @@ static int make_plan(mpr_context* h, int b, int64_t n_local, int d, int kk, Scan
             pl->n_qtiles = (b + q_tile_max - 1) / q_tile_max;
             pl->q_box_rows = q_tile_max;
         }
+        if (pl->q_tmem) pl->q_box_rows = 0;       // nothing of Q in shared memory
         for (pl->cand_cap = kCandCapMax; pl->cand_cap >= 10; pl->cand_cap -= 2) {
             const ScanSmemLayout fixed = scan_smem_layout(pl->n_chunks, pl->q_box_rows, pl->kk_pad, pl->cand_cap, 0);
             stages = (kMaxSmem - 1024 - static_cast<int>(fixed.total)) / kStageBytes;
             if (stages >= 3) break;
         }
         if (pl->cand_cap < 10) pl->cand_cap = 10;
-        if (stages >= 3 || q_tile_max <= 32 || pl->q_box_rows < q_tile_max) break;
+        if (stages >= 3 || q_tile_max <= 32 || pl->q_tmem || pl->q_box_rows < q_tile_max) break;
         q_tile_max >>= 1;
     }
     if (stages > kMaxStages) stages = kMaxStages;
@@ -127,9 +134,11 @@ static int launch_scan(mpr_context* h, const ScanPlan& pl, const uint16_t* q, in
                        const float* bias, int64_t n_local, int64_t idx_base, int d, int kk, uint64_t* part_keys,
                        float* dump, cudaStream_t st) {
     CUtensorMap tq, tb;
-    int rc = encode_2d(h, &tq, q, static_cast<uint64_t>(b), static_cast<uint64_t>(d), pl.q_box_rows);
+    int rc = encode_2d(h, &tq, q, static_cast<uint64_t>(b), static_cast<uint64_t>(d), pl.q_tmem ? 8 : pl.q_box_rows);
     if (rc) return rc;
-    rc = encode_2d(h, &tb, bank, static_cast<uint64_t>(n_local), static_cast<uint64_t>(d), kTileRows);
+    // tensor-bound regime with an even number of q-tiles: CTA pairs share each bank chunk by TMA multicast
+    const bool pair = !kDump && !pl.q_tmem && h->use_cluster && pl.n_qtiles >= 2 && pl.n_qtiles % 2 == 0;
+    rc = encode_2d(h, &tb, bank, static_cast<uint64_t>(n_local), static_cast<uint64_t>(d), pair ? kTileRows / 2 : kTileRows);
     if (rc) return rc;
 
     ScanParams p;
@@ -148,6 +157,8 @@ static int launch_scan(mpr_context* h, const ScanPlan& pl, const uint16_t* q, in
     p.idx_base = static_cast<uint32_t>(idx_base);
     p.bank_policy = pl.n_qtiles == 1 ? ptx::kEvictFirst : ptx::kEvictNormal;
     p.bias = bias;
+    p.q = q;
+    p.d = d;
     p.part_keys = part_keys;
     p.dump = dump;
     p.err = h->d_err;
@@ -155,7 +166,25 @@ static int launch_scan(mpr_context* h, const ScanPlan& pl, const uint16_t* q, in
     const dim3 grid(pl.n_splits * pl.n_qtiles);
     const bool prof = h->prof_used >= 0 && 2 * (h->prof_used + 1) <= static_cast<int>(h->prof_events.size());
     if (prof) CUDA_TRY(h, cudaEventRecord(h->prof_events[2 * h->prof_used], st));
-    scan_topk_kernel<kDump><<<grid, kScanThreads, pl.smem_bytes, st>>>(tq, tb, p);
+    if (pair) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid;
+        cfg.blockDim = dim3(kScanThreads);
+        cfg.dynamicSmemBytes = pl.smem_bytes;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        CUDA_TRY(h, cudaLaunchKernelEx(&cfg, scan_topk_kernel<false, 2, false>, tq, tb, p));
+    } else if (pl.q_tmem) {
+        scan_topk_kernel<kDump, 1, true><<<grid, kScanThreads, pl.smem_bytes, st>>>(tq, tb, p);
+    } else {
+        scan_topk_kernel<kDump, 1, false><<<grid, kScanThreads, pl.smem_bytes, st>>>(tq, tb, p);
+    }
     CUDA_TRY(h, cudaGetLastError());
     if (prof) {
         CUDA_TRY(h, cudaEventRecord(h->prof_events[2 * h->prof_used + 1], st));
@@ -194,9 +223,21 @@ int mpr_create(int device, mpr_handle_t* out) {
     e = cudaMalloc(&h->d_err, sizeof(int));
     if (e == cudaSuccess) e = cudaMemset(h->d_err, 0, sizeof(int));
     if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(scan_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+        e = cudaFuncSetAttribute(scan_topk_kernel<false, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(scan_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+        e = cudaFuncSetAttribute(scan_topk_kernel<true, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(scan_topk_kernel<false, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(scan_topk_kernel<false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(scan_topk_kernel<true, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    {
+        const char* nc = getenv("MPR_NO_CLUSTER");
+        if (nc && nc[0] == '1') h->use_cluster = 0;
+        const char* nq = getenv("MPR_NO_QTMEM");
+        if (nq && nq[0] == '1') h->use_q_tmem = 0;
+    }
     if (e != cudaSuccess) {
         fail(nullptr, MPR_ECUDA, "handle setup failed: %s", cudaGetErrorString(e));
         if (h->d_err) cudaFree(h->d_err);

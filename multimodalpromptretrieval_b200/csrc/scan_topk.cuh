@@ -55,6 +55,8 @@ struct ScanParams {
     uint32_t idx_base; // global row index of this shard's row 0
     uint64_t bank_policy;
     const float* bias;     // [n_local]
+    const uint16_t* q;     // [b_total][d] bf16 queries (read directly in the TMEM-operand variant)
+    int d;                 // row length
     uint64_t* part_keys;   // [b_total][kk][n_splits]
     float* dump;           // debug: [b_total][n_local] scores, or nullptr
     int* err;              // device word that receives the code of a starved barrier
@@ -85,7 +87,18 @@ __host__ __device__ inline ScanSmemLayout scan_smem_layout(int n_chunks, int q_b
 // Barrier error codes (ScanParams::err)
 enum : int { kErrQFull = 101, kErrEmpty = 102, kErrFull = 103, kErrTmemEmpty = 104, kErrTmemFull = 105 };
 
-template <bool kDump>
+// kCluster = 2: the two CTAs of a cluster work on the SAME bank split with DIFFERENT q-tiles; each loads half of every
+// bank K-chunk and TMA-multicasts it into both CTAs' rings, halving the L2->SM traffic per MMA (the limiter of the
+// tensor-bound regime with a resident q-tile: 64 B/cycle/SM of bank per 1-CTA MMA cycle vs ~43 B/cycle/SM available).
+// A ring slot is refilled only after BOTH consumers have released it (multicast tcgen05.commit, empty count = 2).
+//
+// kQTmem: the q-tile lives in TENSOR MEMORY instead of shared memory (columns [0, D/2), D <= 512) and is the MMA's
+// TMEM A operand.  With both operands in shared memory a 128x128x16 MMA reads 8 KiB per 64 cycles = the whole
+// 128 B/cycle shared-memory port, so the TMA writes of the next bank chunks and the MMAs throttle each other
+// (measured 41 % tensor-pipe activity at B=4096 with nothing waiting on data).  With A in TMEM only B crosses the port,
+// and the 128 KiB the q-tile used to occupy go to the bank ring (12 stages instead of 4).  The accumulator ring is
+// then 2 x 128 columns at [256, 512).
+template <bool kDump, int kCluster, bool kQTmem>
 __global__ void __launch_bounds__(kScanThreads, 1)
 scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_bank,
                  const ScanParams p) {
@@ -110,6 +123,8 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    constexpr int kBufs = kQTmem ? 2 : kAccBufs;               // accumulator ring depth
+    constexpr uint32_t kAccCol0 = kQTmem ? 256u : 0u;          // first accumulator column
 
     // ---- which item is this CTA's
     const int item = blockIdx.x;
@@ -123,17 +138,17 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 
     // ---- one-time setup
     if (threadIdx.x == 0) {
-        ptx::mbar_init(bar_q, 1);
+        ptx::mbar_init(bar_q, kQTmem ? 4 : 1);          // TMEM variant: one arrive per epilogue warp
         for (int s = 0; s < p.n_stages; ++s) {
             ptx::mbar_init(bar_full(s), 1);
-            ptx::mbar_init(bar_empty(s), 1);
+            ptx::mbar_init(bar_empty(s), kCluster);      // one release per consumer CTA of the cluster
         }
-        for (int b = 0; b < kAccBufs; ++b) {
+        for (int b = 0; b < kBufs; ++b) {
             ptx::mbar_init(bar_tfull(b), 1);
             ptx::mbar_init(bar_tempty(b), 4);   // one arrive per epilogue warp
         }
         ptx::fence_mbar_init();
-        ptx::prefetch_tensormap(&tmap_q);
+        if constexpr (!kQTmem) ptx::prefetch_tensormap(&tmap_q);
         ptx::prefetch_tensormap(&tmap_bank);
     }
     if (warp == 1) {
@@ -142,59 +157,93 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     }
     ptx::tc_fence_before();
     __syncthreads();
+    if constexpr (kCluster > 1) ptx::cluster_sync();      // peers' barriers exist before anything remote touches them
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const uint32_t crank = kCluster > 1 ? ptx::cluster_ctarank() : 0u;
+    constexpr uint16_t kClusterMask = static_cast<uint16_t>((1u << kCluster) - 1u);
 
+    // Producer and MMA warps run their loops with WARP-UNIFORM control flow (all 32 lanes wait on the barriers together)
+    // and elect one lane only around the asynchronous instructions themselves.  Putting the whole loop under
+    // `if (lane == 0)` makes every operand thread-variant for the compiler: it then wraps each UTCHMMA / UTMALDG in an
+    // election loop with R2UR moves (~130 SASS instructions per K-chunk, measured: MMA issue-bound at 41 % tensor
+    // activity with nothing waiting on data).
     if (warp == 0) {
         // =========================== TMA producer ===========================
-        if (lane == 0) {
-            // resident q-tile: one 128-byte-wide slab per K-chunk
-            const uint32_t slab_bytes = static_cast<uint32_t>(p.q_box_rows) * 128u;
-            ptx::mbar_arrive_expect_tx(bar_q, slab_bytes * p.n_chunks);
-            for (int j = 0; j < p.n_chunks; ++j)
-                ptx::tma_load_2d(q_smem + j * slab_bytes, &tmap_q, bar_q, j * kChunkK, q0, ptx::kEvictLast);
-            // streamed bank
-            int s = 0;
-            uint32_t ph = 0;
-            for (int t = tile_begin; t < tile_end; ++t) {
-                for (int j = 0; j < p.n_chunks; ++j) {
-                    ptx::mbar_wait(bar_empty(s), ph ^ 1u, p.err, kErrEmpty);
+        if constexpr (!kQTmem) {
+            if (ptx::elect_one()) {
+                // resident q-tile: one 128-byte-wide slab per K-chunk
+                const uint32_t slab_bytes = static_cast<uint32_t>(p.q_box_rows) * 128u;
+                ptx::mbar_arrive_expect_tx(bar_q, slab_bytes * p.n_chunks);
+                for (int j = 0; j < p.n_chunks; ++j)
+                    ptx::tma_load_2d(q_smem + j * slab_bytes, &tmap_q, bar_q, j * kChunkK, q0, ptx::kEvictLast);
+            }
+            __syncwarp();
+        }
+        // streamed bank
+        int s = 0;
+        uint32_t ph = 0;
+        for (int t = tile_begin; t < tile_end; ++t) {
+            for (int j = 0; j < p.n_chunks; ++j) {
+                ptx::mbar_wait(bar_empty(s), ph ^ 1u, p.err, kErrEmpty);
+                if (ptx::elect_one()) {
                     ptx::mbar_arrive_expect_tx(bar_full(s), kStageBytes);
-                    ptx::tma_load_2d(stage_smem + s * kStageBytes, &tmap_bank, bar_full(s), j * kChunkK,
-                                     t * kTileRows, p.bank_policy);
-                    if (++s == p.n_stages) { s = 0; ph ^= 1u; }
+                    if constexpr (kCluster > 1) {
+                        // my 1/kCluster of the rows, delivered to every CTA of the cluster
+                        constexpr uint32_t kPart = kStageBytes / kCluster;
+                        ptx::tma_load_2d_multicast(stage_smem + s * kStageBytes + crank * kPart, &tmap_bank, bar_full(s),
+                                                   j * kChunkK, t * kTileRows + crank * (kTileRows / kCluster),
+                                                   kClusterMask, p.bank_policy);
+                    } else {
+                        ptx::tma_load_2d(stage_smem + s * kStageBytes, &tmap_bank, bar_full(s), j * kChunkK,
+                                         t * kTileRows, p.bank_policy);
+                    }
                 }
+                __syncwarp();
+                if (++s == p.n_stages) { s = 0; ph ^= 1u; }
             }
         }
     } else if (warp == 1) {
         // =========================== MMA issuer ===========================
-        if (lane == 0) {
-            constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(kUmmaM, kTileRows);
-            const uint32_t slab_bytes = static_cast<uint32_t>(p.q_box_rows) * 128u;
-            ptx::mbar_wait(bar_q, 0, p.err, kErrQFull);
-            int s = 0;
-            uint32_t ph = 0;
-            for (int lt = 0; lt < my_tiles; ++lt) {
-                const int buf = lt & (kAccBufs - 1);
-                const uint32_t bph = (lt / kAccBufs) & 1u;
-                ptx::mbar_wait(bar_tempty(buf), bph ^ 1u, p.err, kErrTmemEmpty);
+        constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(kUmmaM, kTileRows);
+        // descriptor = constant high word | (address >> 4): advancing by a stage / slab / K-step is an integer add
+        const uint64_t desc_hi = ptx::make_kmajor_sw128_desc(0);
+        const uint32_t b_lo0 = (stage_smem >> 4) & 0x3FFFu;
+        const uint32_t a_lo0 = (q_smem >> 4) & 0x3FFFu;
+        const uint32_t slab_lo = static_cast<uint32_t>(p.q_box_rows) * 8u;      // slab bytes >> 4
+        ptx::mbar_wait(bar_q, 0, p.err, kErrQFull);
+        ptx::tc_fence_after();
+        int s = 0;
+        uint32_t ph = 0;
+        for (int lt = 0; lt < my_tiles; ++lt) {
+            const int buf = lt & (kBufs - 1);
+            const uint32_t bph = (lt / kBufs) & 1u;
+            ptx::mbar_wait(bar_tempty(buf), bph ^ 1u, p.err, kErrTmemEmpty);
+            ptx::tc_fence_after();
+            const uint32_t d_tmem = tmem_base + kAccCol0 + buf * kTileRows;
+            for (int j = 0; j < p.n_chunks; ++j) {
+                ptx::mbar_wait(bar_full(s), ph, p.err, kErrFull);
                 ptx::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + buf * kTileRows;
-                for (int j = 0; j < p.n_chunks; ++j) {
-                    ptx::mbar_wait(bar_full(s), ph, p.err, kErrFull);
-                    ptx::tc_fence_after();
-                    const uint32_t a_addr = q_smem + j * slab_bytes;
-                    const uint32_t b_addr = stage_smem + s * kStageBytes;
+                if (ptx::elect_one()) {
+                    const uint32_t b_lo = b_lo0 + static_cast<uint32_t>(s) * (kStageBytes >> 4);
 #pragma unroll
                     for (int k = 0; k < kChunkK / 16; ++k) {
-                        const uint64_t da = ptx::make_kmajor_sw128_desc(a_addr + k * 32);
-                        const uint64_t db = ptx::make_kmajor_sw128_desc(b_addr + k * 32);
-                        ptx::umma_bf16_ss(d_tmem, da, db, idesc, (j | k) != 0 ? 1u : 0u);
+                        const uint64_t db = desc_hi | static_cast<uint64_t>(b_lo + 2u * k);        // +32 B per K-step
+                        if constexpr (kQTmem) {
+                            // 16 bf16 of K = 8 TMEM columns; chunk j starts at column j*32
+                            ptx::umma_bf16_ts(d_tmem, tmem_base + j * (kChunkK / 2) + k * 8, db, idesc,
+                                              (j | k) != 0 ? 1u : 0u);
+                        } else {
+                            const uint64_t da = desc_hi | static_cast<uint64_t>(a_lo0 + j * slab_lo + 2u * k);
+                            ptx::umma_bf16_ss(d_tmem, da, db, idesc, (j | k) != 0 ? 1u : 0u);
+                        }
                     }
-                    ptx::umma_commit(bar_empty(s));          // smem slot reusable once these MMAs retire
-                    if (++s == p.n_stages) { s = 0; ph ^= 1u; }
+                    if constexpr (kCluster > 1) ptx::umma_commit_multicast(bar_empty(s), kClusterMask);
+                    else ptx::umma_commit(bar_empty(s));     // smem slot reusable once these MMAs retire
+                    if (j == p.n_chunks - 1) ptx::umma_commit(bar_tfull(buf));   // accumulator tile complete
                 }
-                ptx::umma_commit(bar_tfull(buf));            // accumulator tile complete
+                __syncwarp();
+                if (++s == p.n_stages) { s = 0; ph ^= 1u; }
             }
         }
     } else {
@@ -240,6 +289,26 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             if (valid) thr = kth == 0ull ? -CUDART_INF_F : key_score(kth);
         };
 
+        if constexpr (kQTmem) {
+            // This thread's query row -> its TMEM lane, columns [0, D/2): 8 bf16 (one uint4) fill 4 columns.
+            const uint32_t q_taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+            const uint4* qrow = reinterpret_cast<const uint4*>(p.q + static_cast<size_t>(valid ? q0 + row : 0) * p.d);
+            for (int c0 = 0; c0 < p.d / 2; c0 += 32) {
+                uint32_t w[32];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    uint4 t = make_uint4(0u, 0u, 0u, 0u);
+                    if (valid) t = __ldg(qrow + c0 / 4 + u);
+                    w[4 * u + 0] = t.x; w[4 * u + 1] = t.y; w[4 * u + 2] = t.z; w[4 * u + 3] = t.w;
+                }
+                ptx::tmem_st_32x32b_x32(q_taddr + c0, w);
+            }
+            ptx::tmem_wait_st();
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(bar_q);
+        }
+
         auto load_bias = [&](int t) -> float {
             const int r = t * kTileRows + ep_tid;
             return (r < p.n_local) ? __ldg(p.bias + r) : -CUDART_INF_F;   // -inf masks rows past the shard end
@@ -248,8 +317,8 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 
         for (int lt = 0; lt < my_tiles; ++lt) {
             const int t = tile_begin + lt;
-            const int buf = lt & (kAccBufs - 1);
-            const uint32_t bph = (lt / kAccBufs) & 1u;
+            const int buf = lt & (kBufs - 1);
+            const uint32_t bph = (lt / kBufs) & 1u;
             float* bias_tile = bias_s + buf * kTileRows;
             bias_tile[ep_tid] = next_bias;
             ptx::named_bar_sync(1, 128);
@@ -263,7 +332,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 #pragma unroll 1
                 for (int c0 = 0; c0 < kTileRows; c0 += 32) {
                     uint32_t v[32];
-                    ptx::tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
+                    ptx::tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + kAccCol0 +
                                                 buf * kTileRows + c0, v);
                     ptx::tmem_wait_ld();
 #pragma unroll
@@ -327,6 +396,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     __syncwarp();
     ptx::tc_fence_before();
     __syncthreads();
+    if constexpr (kCluster > 1) ptx::cluster_sync();      // no CTA leaves while a peer may still signal its barriers
     if (warp == 1) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc(tmem_base, kTmemCols);
