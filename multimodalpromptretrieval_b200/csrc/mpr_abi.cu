@@ -323,7 +323,7 @@ size_t mpr_search_workspace_bytes(mpr_handle_t h, int b, int64_t n_local, int d,
     if (!h) return 0;
     ScanPlan pl;
     if (make_plan(h, b, n_local, d, kk, &pl)) return 0;
-    return static_cast<size_t>(pl.n_splits) * b * kk * sizeof(uint64_t);
+    return static_cast<size_t>(pl.n_splits) * kEpiGroups * b * kk * sizeof(uint64_t);
 }
 
 int mpr_search_plan(mpr_handle_t h, int b, int64_t n_local, int d, int kk, int* n_ctas, int* n_splits, int* n_qtiles,
@@ -352,7 +352,7 @@ int mpr_search_topk(mpr_handle_t h, const uint16_t* q, int b, const uint16_t* ba
     ScanPlan pl;
     int rc = make_plan(h, b, n_local, d, kk, &pl);
     if (rc) return rc;
-    const size_t need = static_cast<size_t>(pl.n_splits) * b * kk * sizeof(uint64_t);
+    const size_t need = static_cast<size_t>(pl.n_splits) * kEpiGroups * b * kk * sizeof(uint64_t);
     if (workspace_bytes < need)
         return fail(h, MPR_EWORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, need);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -361,8 +361,8 @@ int mpr_search_topk(mpr_handle_t h, const uint16_t* q, int b, const uint16_t* ba
     if (rc) return rc;
     const int warps_per_block = 4;
     merge_topk_kernel<<<(b + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(
-        part, pl.n_splits, 1ll, static_cast<long long>(kk) * pl.n_splits, static_cast<long long>(pl.n_splits), b, kk,
-        out_keys, out_score, out_idx);
+        part, pl.n_splits * kEpiGroups, 1ll, static_cast<long long>(kk) * pl.n_splits * kEpiGroups,
+        static_cast<long long>(pl.n_splits) * kEpiGroups, b, kk, out_keys, out_score, out_idx);
     CUDA_TRY(h, cudaGetLastError());
     return MPR_OK;
 }
@@ -456,7 +456,7 @@ int mpr_debug_scores(mpr_handle_t h, const uint16_t* q, int b, const uint16_t* b
     ScanPlan pl;
     int rc = make_plan(h, b, n_local, d, 1, &pl);
     if (rc) return rc;
-    const size_t need = static_cast<size_t>(pl.n_splits) * b * sizeof(uint64_t);
+    const size_t need = static_cast<size_t>(pl.n_splits) * kEpiGroups * b * sizeof(uint64_t);
     if (workspace_bytes < need) return fail(h, MPR_EWORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, need);
     return launch_scan<true>(h, pl, q, b, bank, bias, n_local, 0, d, 1, static_cast<uint64_t*>(workspace), scores,
                              static_cast<cudaStream_t>(stream));

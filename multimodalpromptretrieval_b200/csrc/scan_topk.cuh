@@ -14,8 +14,9 @@
 // CTAs resident at the same time share a bank range and all but the first read of it hit L2.  The q-tile
 // (<= 128 queries, <= 128 KiB) is loaded once and stays resident in shared memory; only the bank streams.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
-// warps 2..5 = epilogue (warp w reads TMEM lanes 32*(w%4)...).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected lane),
+// warps 2..9 = two epilogue groups of four warps (warp w reads TMEM lanes 32*(w%4)...); group g takes tiles g, g+2, ...
+// and keeps its own per-query lists, so a tile's epilogue may take two MMA tile-times before it stalls the pipe.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -33,10 +34,11 @@ constexpr int kChunkK = 64;                   // bf16 per 128-byte swizzled row
 constexpr int kStageBytes = kTileRows * 128;  // one bank K-chunk: 128 rows x 128 B = 16 KiB
 constexpr int kAccBufs = 4;                   // TMEM accumulator ring: 4 x 128 columns
 constexpr int kTmemCols = 512;
-constexpr int kScanThreads = 192;
+constexpr int kScanThreads = 320;            // warp 0 TMA, warp 1 MMA, warps 2..9 = two epilogue groups of four
 constexpr int kMaxStages = 12;
 constexpr int kMaxSmem = 232448;              // 227 KiB opt-in limit per CTA on sm_100
 constexpr int kMaxKK = 32;
+constexpr int kEpiGroups = 2;                 // epilogue groups; group g owns tiles g, g+2, ... (own lists per query)
 constexpr int kCandCapMax = 16;               // per-query pending-candidate slots (a flush leaves >= 8 free)
 
 struct ScanParams {
@@ -57,7 +59,7 @@ struct ScanParams {
     const float* bias;     // [n_local]
     const uint16_t* q;     // [b_total][d] bf16 queries (read directly in the TMEM-operand variant)
     int d;                 // row length
-    uint64_t* part_keys;   // [b_total][kk][n_splits]
+    uint64_t* part_keys;   // [b_total][kk][n_splits * kEpiGroups]
     float* dump;           // debug: [b_total][n_local] scores, or nullptr
     int* err;              // device word that receives the code of a starved barrier
 };
@@ -78,7 +80,7 @@ __host__ __device__ inline ScanSmemLayout scan_smem_layout(int n_chunks, int q_b
     l.q_off = 0;
     l.stage_off = static_cast<uint32_t>(n_chunks) * q_box_rows * 128u;          // multiple of 1024
     l.list_off = l.stage_off + static_cast<uint32_t>(n_stages) * kStageBytes;
-    l.bias_off = l.list_off + static_cast<uint32_t>(kUmmaM) * scan_row_stride(kk_pad, cand_cap) * 8u;
+    l.bias_off = l.list_off + static_cast<uint32_t>(kEpiGroups * kUmmaM) * scan_row_stride(kk_pad, cand_cap) * 8u;
     l.bar_off = l.bias_off + kAccBufs * kTileRows * 4u;
     l.total = l.bar_off + (1 + 2 * kMaxStages + 2 * kAccBufs) * 8u + 16u;
     return l;
@@ -252,14 +254,15 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         // admission threshold (score of its current kk-th best) in a register, appends the rare scores that beat it
         // to its own pending buffer in shared memory, and — when some lane's buffer runs full — every lane folds
         // its own pending candidates into its own sorted list.  No cross-lane traffic except one vote per 8 scores.
+        const int grp = (warp - 2) >> 2;               // epilogue group: owns tiles grp, grp + 2, ...
         const int quad = warp & 3;                     // TMEM lane quadrant this warp may read
         const int row = quad * 32 + lane;              // query slot (TMEM lane) owned by this thread
         const bool valid = row < q_valid;
         const bool warp_has_work = quad * 32 < q_valid;
-        const int ep_tid = (warp - 2) * 32 + lane;     // 0..127, used to stage the bias tile
+        const int ep_tid = ((warp - 2) & 3) * 32 + lane;   // 0..127 within the group, used to stage the bias tile
         const int kk = p.kk;
         const int kk_pad = p.kk_pad;
-        uint64_t* my_list = lists + static_cast<size_t>(row) * scan_row_stride(kk_pad, p.cand_cap);   // [0, kk) sorted keys
+        uint64_t* my_list = lists + static_cast<size_t>(grp * kUmmaM + row) * scan_row_stride(kk_pad, p.cand_cap);   // [0, kk)
         uint2* my_pend = reinterpret_cast<uint2*>(my_list + kk_pad);                      // (score bits, row)
         for (int i = 0; i < kk; ++i) my_list[i] = 0ull;
         float thr = valid ? -CUDART_INF_F : CUDART_INF_F;
@@ -289,7 +292,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             if (valid) thr = kth == 0ull ? -CUDART_INF_F : key_score(kth);
         };
 
-        if constexpr (kQTmem) {
+        if (kQTmem && grp == 0) {
             // This thread's query row -> its TMEM lane, columns [0, D/2): 8 bf16 (one uint4) fill 4 columns.
             const uint32_t q_taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
             const uint4* qrow = reinterpret_cast<const uint4*>(p.q + static_cast<size_t>(valid ? q0 + row : 0) * p.d);
@@ -313,16 +316,17 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             const int r = t * kTileRows + ep_tid;
             return (r < p.n_local) ? __ldg(p.bias + r) : -CUDART_INF_F;   // -inf masks rows past the shard end
         };
-        float next_bias = my_tiles > 0 ? load_bias(tile_begin) : 0.f;
+        float next_bias = grp < my_tiles ? load_bias(tile_begin + grp) : 0.f;
 
-        for (int lt = 0; lt < my_tiles; ++lt) {
+        for (int lt = grp; lt < my_tiles; lt += kEpiGroups) {
             const int t = tile_begin + lt;
             const int buf = lt & (kBufs - 1);
             const uint32_t bph = (lt / kBufs) & 1u;
-            float* bias_tile = bias_s + buf * kTileRows;
+            // bias tiles are double-buffered per group: a fast warp may stage tile lt+2 while a slow one still reads lt
+            float* bias_tile = bias_s + (grp * 2 + ((lt >> 1) & 1)) * kTileRows;
             bias_tile[ep_tid] = next_bias;
-            ptx::named_bar_sync(1, 128);
-            if (lt + 1 < my_tiles) next_bias = load_bias(t + 1);
+            ptx::named_bar_sync(1 + grp, 128);
+            if (lt + kEpiGroups < my_tiles) next_bias = load_bias(t + kEpiGroups);
 
             ptx::mbar_wait(bar_tfull(buf), bph, p.err, kErrTmemFull);
             ptx::tc_fence_after();
@@ -381,13 +385,14 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             if (lane == 0) ptx::mbar_arrive(bar_tempty(buf));
         }
 
-        // partial result of this (split, q-tile): part_keys[q0 + row][rank][split] — rank-major per query, so the
-        // merge kernel's walk over all splits' rank-i candidates is one contiguous stream
+        // partial result of this (split, group, q-tile): part_keys[q0 + row][rank][split * 2 + grp] — rank-major per
+        // query, so the merge kernel's walk over all lists' rank-i candidates is one contiguous stream
         if (warp_has_work) {
             flush();
             if (valid) {
-                uint64_t* dst = p.part_keys + static_cast<size_t>(q0 + row) * kk * p.n_splits + split;
-                for (int i = 0; i < kk; ++i) dst[static_cast<size_t>(i) * p.n_splits] = my_list[i];
+                const size_t n_lists = static_cast<size_t>(p.n_splits) * kEpiGroups;
+                uint64_t* dst = p.part_keys + static_cast<size_t>(q0 + row) * kk * n_lists + split * kEpiGroups + grp;
+                for (int i = 0; i < kk; ++i) dst[static_cast<size_t>(i) * n_lists] = my_list[i];
             }
         }
     }
