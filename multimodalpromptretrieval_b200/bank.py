@@ -14,6 +14,8 @@ Differences from the reference that a caller can observe (all documented in DESI
 """
 from __future__ import annotations
 
+import hashlib
+import json
 import os
 import pickle
 import weakref
@@ -24,7 +26,7 @@ import torch
 
 from . import kernels as K
 from .prompt import PromptTables, bucket_lut, prompt_string
-from .sharding import CandidateExchange, P2PExchange, shard_bounds
+from .sharding import CandidateExchange, P2PExchange, plan_shard_reads, shard_bounds
 
 _INFO_KEYS = ("question_type", "question_id", "question")
 
@@ -244,6 +246,73 @@ class RetrievalBank:
         self._tables = None
         self._memo = None
         self._graphs = {}
+
+    # ------------------------------------------------------------------------------------------ shard cache (N2)
+    SHARD_FORMAT = 1
+
+    @staticmethod
+    def cache_key(**parts) -> str:
+        """Key for the shard cache.  The reference keys its cache on the dataset CLASS NAME only
+        (VQAFeatureDataset.py:122-124), so a changed split / subset / union / CLIP checkpoint silently reuses a stale
+        bank; here the caller lists what the bank depends on and the manifest refuses a mismatch."""
+        return hashlib.sha1(json.dumps(parts, sort_keys=True, default=str).encode()).hexdigest()[:16]
+
+    def save_shards(self, directory: str, key: str = "") -> None:
+        """Writes this rank's rows exactly as they sit in HBM — ``shard_<rank>.bf16`` (raw bf16 row-major) and
+        ``bias_<rank>.f32`` — plus, on rank 0, the interned answers, the info dict and ``manifest.json``.  Loading
+        needs no cast and no CLIP pass, and works for any later GPU count (files are addressed by row range)."""
+        os.makedirs(directory, exist_ok=True)
+        r, w = self.exchange.rank, self.exchange.world_size
+        self.retrieval_embeddings.view(torch.int16).cpu().numpy().tofile(os.path.join(directory, f"shard_{r:03d}.bf16"))
+        self.bias.cpu().numpy().tofile(os.path.join(directory, f"bias_{r:03d}.f32"))
+        if r == 0:
+            self.answer_id.cpu().numpy().tofile(os.path.join(directory, "answer_id.i32"))
+            with open(os.path.join(directory, "meta.pkl"), "wb") as f:
+                pickle.dump({"answer_strings": self.answer_strings, "info": self.retrieval_question_info}, f)
+            manifest = {"format": self.SHARD_FORMAT, "key": key, "n_total": self.n_total, "dim": self.dim,
+                        "normalise": self.normalise, "world_size": w,
+                        "ranges": [list(shard_bounds(self.n_total, i, w)) for i in range(w)]}
+            with open(os.path.join(directory, "manifest.json"), "w") as f:
+                json.dump(manifest, f)
+
+    def load_shards(self, directory: str, key: str = "", is_training_phase: Optional[bool] = None,
+                    retrieval_k: Optional[int] = None) -> bool:
+        """Loads this rank's rows from a shard directory written by :meth:`save_shards` under ANY world size.
+        Returns False (and loads nothing) if there is no manifest or it does not match ``key`` / ``normalise``."""
+        path = os.path.join(directory, "manifest.json")
+        if not os.path.exists(path):
+            return False
+        with open(path) as f:
+            m = json.load(f)
+        if m.get("format") != self.SHARD_FORMAT or m.get("key", "") != key or bool(m["normalise"]) != self.normalise:
+            return False
+        n_total, dim = int(m["n_total"]), int(m["dim"])
+        begin, end = shard_bounds(n_total, self.exchange.rank, self.exchange.world_size)
+        n_local = end - begin
+        bank = torch.empty((max(n_local, 1), dim), dtype=torch.bfloat16, device=self.device)[:n_local]
+        bias = torch.empty((max(n_local, 1),), dtype=torch.float32, device=self.device)[:n_local]
+        for i, first, n, dst in plan_shard_reads([tuple(x) for x in m["ranges"]], begin, end):
+            rows = np.memmap(os.path.join(directory, f"shard_{i:03d}.bf16"), dtype=np.int16, mode="r",
+                             offset=first * dim * 2, shape=(n, dim))
+            bank[dst:dst + n].view(torch.int16).copy_(torch.from_numpy(np.ascontiguousarray(rows)))
+            b = np.memmap(os.path.join(directory, f"bias_{i:03d}.f32"), dtype=np.float32, mode="r",
+                          offset=first * 4, shape=(n,))
+            bias[dst:dst + n].copy_(torch.from_numpy(np.ascontiguousarray(b)))
+        with open(os.path.join(directory, "meta.pkl"), "rb") as f:
+            meta = pickle.load(f)
+        ids = np.fromfile(os.path.join(directory, "answer_id.i32"), dtype=np.int32)
+        if is_training_phase is not None:
+            self.is_training_phase = is_training_phase
+        if retrieval_k is not None:
+            self.retrieval_k = retrieval_k
+        self.retrieval_embeddings, self.bias = bank, bias
+        self.n_total, self.dim, self.row_begin = n_total, dim, begin
+        self.answer_strings = list(meta["answer_strings"])
+        self.retrieval_question_info = {k: list(v) for k, v in meta["info"].items()}
+        self.retrieval_answers = _AnswerView(ids, self.answer_strings)
+        self.answer_id = torch.from_numpy(ids).to(self.device)
+        self._tables, self._memo, self._graphs = None, None, {}
+        return True
 
     # ------------------------------------------------------------------------------------------ query path
     def _encode(self, batch) -> Tuple[torch.Tensor, torch.Tensor]:

@@ -28,6 +28,20 @@ def owner_of_row(row: int, n_rows: int, world_size: int) -> int:
     return row // per
 
 
+def plan_shard_reads(file_ranges, begin: int, end: int):
+    """Which slices of which shard files cover rows [begin, end)?  ``file_ranges`` = [(row_begin, row_end), ...] of
+    the files in a shard directory (any world size); returns [(file_index, first_row_in_file, n_rows, dst_offset)]."""
+    out = []
+    for i, (fb, fe) in enumerate(file_ranges):
+        lo, hi = max(begin, fb), min(end, fe)
+        if lo < hi:
+            out.append((i, lo - fb, hi - lo, lo - begin))
+    covered = sum(n for _, _, n, _ in out)
+    if covered != max(0, end - begin):
+        raise ValueError(f"shard files cover {covered} of the {end - begin} rows [{begin}, {end})")
+    return out
+
+
 class CandidateExchange:
     """All-gather of each rank's candidate keys ``[B, kk]`` (int64 view of u64) into ``[world, B, kk]``.
 

@@ -438,3 +438,34 @@ def test_p2p_exchange_protocol_on_one_gpu(K, world):
             ctrl = bufs[r][:8].cpu().numpy().view(np.uint32)
             assert ctrl[0] == step + 1 and ctrl[1] == 0                    # epoch published, done-counter reset
     assert K.handle(0).device_error() == 0
+
+
+def test_shard_cache_roundtrip_and_resharding(tmp_path, golden_cases, tokenizer):
+    """N2: the bank is saved exactly as laid out in HBM (bf16 shards + bias + interned answers) and reloaded without a
+    cast or a CLIP pass — under the same or a different world size — with identical retrieval results."""
+    from multimodalpromptretrieval_b200.bank import RetrievalBank
+    g = golden_cases["k5_train"]
+    src, batch = _bank_from_golden(g, tokenizer)
+    key = RetrievalBank.cache_key(dataset="golden", split="train", normalise=False)
+    # save as if 3 ranks had written (rank/world are plain attributes of the exchange object)
+    for r in range(3):
+        part, _ = _bank_from_golden(g, tokenizer)
+        part.exchange.rank, part.exchange.world_size = r, 3
+        part.install_bank([(g.bank_img, g.bank_txt)], g.answers, g.info, is_training_phase=g.training, retrieval_k=g.k)
+        part.save_shards(str(tmp_path / "shards"), key)
+    loaded, _ = _bank_from_golden(g, tokenizer)
+    loaded.retrieval_embeddings = None
+    assert not loaded.load_shards(str(tmp_path / "shards"), key="other-key")
+    assert loaded.load_shards(str(tmp_path / "shards"), key, is_training_phase=g.training, retrieval_k=g.k)
+    assert torch.equal(loaded.retrieval_embeddings, src.retrieval_embeddings) and torch.equal(loaded.bias, src.bias)
+    assert loaded.retrieve_closest_qa_pairs(batch) == g.j["prompts_quant"]
+    assert loaded.retrieve_closest_qa_pairs(batch, return_info=["question", "question_id"]) == g.j["return_info_q_id"]
+    ids, _ = loaded.retrieve_prompt_ids(batch)
+    assert np.array_equal(ids.cpu().numpy(), g.z["input_ids_quant"])
+    # a 2-rank job reading the 3-rank files: each rank gets exactly its contiguous rows
+    for r in range(2):
+        part, _ = _bank_from_golden(g, tokenizer)
+        part.exchange.rank, part.exchange.world_size = r, 2
+        assert part.load_shards(str(tmp_path / "shards"), key)
+        b0, b1 = part.row_begin, part.row_begin + part.retrieval_embeddings.shape[0]
+        assert torch.equal(part.retrieval_embeddings, src.retrieval_embeddings[b0:b1])

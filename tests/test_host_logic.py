@@ -132,3 +132,23 @@ def test_fast_prefix_tokenisation_equals_hf_tokenizer(tokenizer):
         ref = tokenizer(prompt.prefix_texts(tasks, questions, quant), add_special_tokens=False)["input_ids"]
         assert [ids[off[i]:off[i + 1]].tolist() for i in range(len(questions))] == ref
     assert tables.tail_bound(True) > tables.tail_bound(False) - 8 and tables.max_answer_len >= 1
+
+
+def test_plan_shard_reads_reshards_across_world_sizes():
+    n = 1003
+    for w_saved in (1, 2, 3, 8):
+        files = [sharding.shard_bounds(n, r, w_saved) for r in range(w_saved)]
+        for w_load in (1, 2, 4, 5):
+            seen = []
+            for r in range(w_load):
+                b, e = sharding.shard_bounds(n, r, w_load)
+                plan = sharding.plan_shard_reads(files, b, e)
+                pos = 0
+                for i, first, cnt, dst in plan:
+                    assert dst == pos and files[i][0] + first == b + dst and first + cnt <= files[i][1] - files[i][0]
+                    pos += cnt
+                    seen.extend(range(files[i][0] + first, files[i][0] + first + cnt))
+                assert pos == e - b
+            assert seen == list(range(n))
+    with pytest.raises(ValueError):
+        sharding.plan_shard_reads([(0, 10)], 5, 20)
