@@ -29,6 +29,7 @@ struct mpr_context {
     int* d_err = nullptr;
     PFN_encodeTiled encode = nullptr;
     std::vector<cudaEvent_t> prof_events;   // start/stop pairs, used only between mpr_profile_begin/end
+    int stage_subs = 2;                     // 64-wide K sub-chunks per ring stage (MPR_STAGE_SUBS=1|2)
     int use_q_tmem = 1;                     // q-tile as TMEM A operand when D <= 512 (MPR_NO_QTMEM=1 disables)
     int use_cluster = 1;                    // CTA-pair TMA multicast in the tensor-bound regime (MPR_NO_CLUSTER=1 disables)
     int prof_used = -1;                     // -1 = profiling off
@@ -59,7 +60,7 @@ static inline int pow2_ceil(int v) { int p = 1; while (p < v) p <<= 1; return p;
 
 // ------------------------------------------------------------------------------------------------ planning
 struct ScanPlan {
-    int n_chunks, q_tile, q_box_rows, n_qtiles, n_splits, n_tiles, n_stages, kk_pad, cand_cap;
+    int n_chunks, q_tile, q_box_rows, n_qtiles, n_splits, n_tiles, n_stages, kk_pad, cand_cap, sub_per_stage;
     bool q_tmem;       // q-tile in tensor memory (TMEM A operand) instead of shared memory
     uint32_t smem_bytes;
 };
@@ -94,23 +95,27 @@ static int make_plan(mpr_context* h, int b, int64_t n_local, int d, int kk, Scan
         }
         if (pl->q_tmem) pl->q_box_rows = 0;       // nothing of Q in shared memory
         for (pl->cand_cap = kCandCapMax; pl->cand_cap >= 10; pl->cand_cap -= 2) {
-            const ScanSmemLayout fixed = scan_smem_layout(pl->n_chunks, pl->q_box_rows, pl->kk_pad, pl->cand_cap, 0);
-            stages = (kMaxSmem - 1024 - static_cast<int>(fixed.total)) / kStageBytes;
+            const ScanSmemLayout fixed = scan_smem_layout(pl->n_chunks, pl->q_box_rows, pl->kk_pad, pl->cand_cap, 0, 1);
+            stages = (kMaxSmem - 1024 - static_cast<int>(fixed.total)) / kStageBytes;     // in 16 KiB units
             if (stages >= 3) break;
         }
         if (pl->cand_cap < 10) pl->cand_cap = 10;
         if (stages >= 3 || q_tile_max <= 32 || pl->q_tmem || pl->q_box_rows < q_tile_max) break;
         q_tile_max >>= 1;
     }
-    if (stages > kMaxStages) stages = kMaxStages;
     if (stages < 2) return fail(h, MPR_EINVAL, "shape does not fit shared memory (d=%d, kk=%d)", d, kk);
+    // Pair 64-wide K sub-chunks into 32 KiB ring stages (one barrier round-trip per 8 MMAs) when at least three such
+    // stages fit; otherwise keep 16 KiB stages.
+    pl->sub_per_stage = (h->stage_subs == 2 && pl->n_chunks >= 2 && stages >= 6) ? 2 : 1;
+    stages /= pl->sub_per_stage;
+    if (stages > kMaxStages) stages = kMaxStages;
     pl->n_stages = stages;
     // items = n_splits * n_qtiles should be a whole number of waves over the SMs
     const int g = std::gcd(h->num_sms, pl->n_qtiles);
     pl->n_splits = h->num_sms / g;
     if (pl->n_splits > pl->n_tiles) pl->n_splits = pl->n_tiles;
     if (pl->n_splits < 1) pl->n_splits = 1;
-    pl->smem_bytes = scan_smem_layout(pl->n_chunks, pl->q_box_rows, pl->kk_pad, pl->cand_cap, stages).total + 1024u;
+    pl->smem_bytes = scan_smem_layout(pl->n_chunks, pl->q_box_rows, pl->kk_pad, pl->cand_cap, stages, pl->sub_per_stage).total + 1024u;
     return MPR_OK;
 }
 
@@ -154,6 +159,7 @@ static int launch_scan(mpr_context* h, const ScanPlan& pl, const uint16_t* q, in
     p.n_splits = pl.n_splits;
     p.n_tiles = pl.n_tiles;
     p.n_stages = pl.n_stages;
+    p.sub_per_stage = pl.sub_per_stage;
     p.idx_base = static_cast<uint32_t>(idx_base);
     p.bank_policy = pl.n_qtiles == 1 ? ptx::kEvictFirst : ptx::kEvictNormal;
     p.bias = bias;
@@ -235,6 +241,8 @@ int mpr_create(int device, mpr_handle_t* out) {
     {
         const char* nc = getenv("MPR_NO_CLUSTER");
         if (nc && nc[0] == '1') h->use_cluster = 0;
+        const char* ss = getenv("MPR_STAGE_SUBS");
+        if (ss && (ss[0] == '1' || ss[0] == '2')) h->stage_subs = ss[0] - '0';
         const char* nq = getenv("MPR_NO_QTMEM");
         if (nq && nq[0] == '1') h->use_q_tmem = 0;
     }

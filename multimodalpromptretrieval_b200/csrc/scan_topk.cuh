@@ -54,6 +54,7 @@ struct ScanParams {
     int n_splits;
     int n_tiles;       // ceil(n_local / 128)
     int n_stages;
+    int sub_per_stage; // 64-wide K sub-chunks per ring stage (1 or 2): one barrier round-trip per stage
     uint32_t idx_base; // global row index of this shard's row 0
     uint64_t bank_policy;
     const float* bias;     // [n_local]
@@ -75,11 +76,11 @@ __host__ __device__ inline uint32_t scan_row_stride(int kk_pad, int cand_cap) {
 }
 
 __host__ __device__ inline ScanSmemLayout scan_smem_layout(int n_chunks, int q_box_rows, int kk_pad, int cand_cap,
-                                                           int n_stages) {
+                                                           int n_stages, int sub_per_stage) {
     ScanSmemLayout l;
     l.q_off = 0;
     l.stage_off = static_cast<uint32_t>(n_chunks) * q_box_rows * 128u;          // multiple of 1024
-    l.list_off = l.stage_off + static_cast<uint32_t>(n_stages) * kStageBytes;
+    l.list_off = l.stage_off + static_cast<uint32_t>(n_stages) * sub_per_stage * kStageBytes;
     l.bias_off = l.list_off + static_cast<uint32_t>(kEpiGroups * kUmmaM) * scan_row_stride(kk_pad, cand_cap) * 8u;
     l.bar_off = l.bias_off + kAccBufs * kTileRows * 4u;
     l.total = l.bar_off + (1 + 2 * kMaxStages + 2 * kAccBufs) * 8u + 16u;
@@ -109,7 +110,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const uint32_t base = (raw_addr + 1023u) & ~1023u;   // SWIZZLE_128B atoms need 1024-byte alignment
     uint8_t* smem = smem_raw + (base - raw_addr);
 
-    const ScanSmemLayout lay = scan_smem_layout(p.n_chunks, p.q_box_rows, p.kk_pad, p.cand_cap, p.n_stages);
+    const ScanSmemLayout lay = scan_smem_layout(p.n_chunks, p.q_box_rows, p.kk_pad, p.cand_cap, p.n_stages, p.sub_per_stage);
     const uint32_t q_smem = base + lay.q_off;
     const uint32_t stage_smem = base + lay.stage_off;
     uint64_t* lists = reinterpret_cast<uint64_t*>(smem + lay.list_off);
@@ -182,23 +183,28 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             }
             __syncwarp();
         }
-        // streamed bank
+        // streamed bank: a ring stage holds up to sub_per_stage 64-wide K sub-chunks and costs ONE barrier round-trip
+        const int spp = p.sub_per_stage;
         int s = 0;
         uint32_t ph = 0;
         for (int t = tile_begin; t < tile_end; ++t) {
-            for (int j = 0; j < p.n_chunks; ++j) {
+            for (int j0 = 0; j0 < p.n_chunks; j0 += spp) {
+                const int ns = min(spp, p.n_chunks - j0);
                 ptx::mbar_wait(bar_empty(s), ph ^ 1u, p.err, kErrEmpty);
                 if (ptx::elect_one()) {
-                    ptx::mbar_arrive_expect_tx(bar_full(s), kStageBytes);
-                    if constexpr (kCluster > 1) {
-                        // my 1/kCluster of the rows, delivered to every CTA of the cluster
-                        constexpr uint32_t kPart = kStageBytes / kCluster;
-                        ptx::tma_load_2d_multicast(stage_smem + s * kStageBytes + crank * kPart, &tmap_bank, bar_full(s),
-                                                   j * kChunkK, t * kTileRows + crank * (kTileRows / kCluster),
-                                                   kClusterMask, p.bank_policy);
-                    } else {
-                        ptx::tma_load_2d(stage_smem + s * kStageBytes, &tmap_bank, bar_full(s), j * kChunkK,
-                                         t * kTileRows, p.bank_policy);
+                    ptx::mbar_arrive_expect_tx(bar_full(s), ns * kStageBytes);
+                    for (int u = 0; u < ns; ++u) {
+                        const uint32_t dst = stage_smem + (s * spp + u) * kStageBytes;
+                        if constexpr (kCluster > 1) {
+                            // my 1/kCluster of the rows, delivered to every CTA of the cluster
+                            constexpr uint32_t kPart = kStageBytes / kCluster;
+                            ptx::tma_load_2d_multicast(dst + crank * kPart, &tmap_bank, bar_full(s), (j0 + u) * kChunkK,
+                                                       t * kTileRows + crank * (kTileRows / kCluster), kClusterMask,
+                                                       p.bank_policy);
+                        } else {
+                            ptx::tma_load_2d(dst, &tmap_bank, bar_full(s), (j0 + u) * kChunkK, t * kTileRows,
+                                             p.bank_policy);
+                        }
                     }
                 }
                 __syncwarp();
@@ -215,6 +221,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         const uint32_t slab_lo = static_cast<uint32_t>(p.q_box_rows) * 8u;      // slab bytes >> 4
         ptx::mbar_wait(bar_q, 0, p.err, kErrQFull);
         ptx::tc_fence_after();
+        const int spp = p.sub_per_stage;
         int s = 0;
         uint32_t ph = 0;
         for (int lt = 0; lt < my_tiles; ++lt) {
@@ -223,26 +230,33 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             ptx::mbar_wait(bar_tempty(buf), bph ^ 1u, p.err, kErrTmemEmpty);
             ptx::tc_fence_after();
             const uint32_t d_tmem = tmem_base + kAccCol0 + buf * kTileRows;
-            for (int j = 0; j < p.n_chunks; ++j) {
+            for (int j0 = 0; j0 < p.n_chunks; j0 += spp) {
+                const int ns = min(spp, p.n_chunks - j0);
                 ptx::mbar_wait(bar_full(s), ph, p.err, kErrFull);
                 ptx::tc_fence_after();
                 if (ptx::elect_one()) {
-                    const uint32_t b_lo = b_lo0 + static_cast<uint32_t>(s) * (kStageBytes >> 4);
 #pragma unroll
-                    for (int k = 0; k < kChunkK / 16; ++k) {
-                        const uint64_t db = desc_hi | static_cast<uint64_t>(b_lo + 2u * k);        // +32 B per K-step
-                        if constexpr (kQTmem) {
-                            // 16 bf16 of K = 8 TMEM columns; chunk j starts at column j*32
-                            ptx::umma_bf16_ts(d_tmem, tmem_base + j * (kChunkK / 2) + k * 8, db, idesc,
-                                              (j | k) != 0 ? 1u : 0u);
-                        } else {
-                            const uint64_t da = desc_hi | static_cast<uint64_t>(a_lo0 + j * slab_lo + 2u * k);
-                            ptx::umma_bf16_ss(d_tmem, da, db, idesc, (j | k) != 0 ? 1u : 0u);
+                    for (int u = 0; u < 2; ++u) {
+                        if (u < ns) {
+                            const int j = j0 + u;
+                            const uint32_t b_lo = b_lo0 + static_cast<uint32_t>(s * spp + u) * (kStageBytes >> 4);
+#pragma unroll
+                            for (int k = 0; k < kChunkK / 16; ++k) {
+                                const uint64_t db = desc_hi | static_cast<uint64_t>(b_lo + 2u * k);   // +32 B per K-step
+                                if constexpr (kQTmem) {
+                                    // 16 bf16 of K = 8 TMEM columns; sub-chunk j starts at column j*32
+                                    ptx::umma_bf16_ts(d_tmem, tmem_base + j * (kChunkK / 2) + k * 8, db, idesc,
+                                                      (j | k) != 0 ? 1u : 0u);
+                                } else {
+                                    const uint64_t da = desc_hi | static_cast<uint64_t>(a_lo0 + j * slab_lo + 2u * k);
+                                    ptx::umma_bf16_ss(d_tmem, da, db, idesc, (j | k) != 0 ? 1u : 0u);
+                                }
+                            }
                         }
                     }
                     if constexpr (kCluster > 1) ptx::umma_commit_multicast(bar_empty(s), kClusterMask);
-                    else ptx::umma_commit(bar_empty(s));     // smem slot reusable once these MMAs retire
-                    if (j == p.n_chunks - 1) ptx::umma_commit(bar_tfull(buf));   // accumulator tile complete
+                    else ptx::umma_commit(bar_empty(s));     // ring stage reusable once these MMAs retire
+                    if (j0 + ns == p.n_chunks) ptx::umma_commit(bar_tfull(buf));   // accumulator tile complete
                 }
                 __syncwarp();
                 if (++s == p.n_stages) { s = 0; ph ^= 1u; }
