@@ -29,7 +29,7 @@ struct mpr_context {
     int* d_err = nullptr;
     PFN_encodeTiled encode = nullptr;
     std::vector<cudaEvent_t> prof_events;   // start/stop pairs, used only between mpr_profile_begin/end
-    int stage_subs = 2;                     // 64-wide K sub-chunks per ring stage (MPR_STAGE_SUBS=1|2)
+    int stage_subs = 4;                     // max 64-wide K sub-chunks per ring stage (MPR_STAGE_SUBS=1|2|4)
     int use_q_tmem = 1;                     // q-tile as TMEM A operand when D <= 512 (MPR_NO_QTMEM=1 disables)
     int use_cluster = 1;                    // CTA-pair TMA multicast in the tensor-bound regime (MPR_NO_CLUSTER=1 disables)
     int prof_used = -1;                     // -1 = profiling off
@@ -104,9 +104,11 @@ static int make_plan(mpr_context* h, int b, int64_t n_local, int d, int kk, Scan
         q_tile_max >>= 1;
     }
     if (stages < 2) return fail(h, MPR_EINVAL, "shape does not fit shared memory (d=%d, kk=%d)", d, kk);
-    // Pair 64-wide K sub-chunks into 32 KiB ring stages (one barrier round-trip per 8 MMAs) when at least three such
-    // stages fit; otherwise keep 16 KiB stages.
-    pl->sub_per_stage = (h->stage_subs == 2 && pl->n_chunks >= 2 && stages >= 6) ? 2 : 1;
+    // Group 64-wide K sub-chunks into 32 / 64 KiB ring stages (one barrier round-trip per 8 / 16 MMAs — the MMA warp is
+    // otherwise bound by its own barrier + issue overhead) as long as at least three stages remain.
+    pl->sub_per_stage = 1;
+    if (h->stage_subs >= 2 && pl->n_chunks >= 2 && stages >= 6) pl->sub_per_stage = 2;
+    if (h->stage_subs >= 4 && pl->n_chunks >= 4 && stages >= 12) pl->sub_per_stage = 4;
     stages /= pl->sub_per_stage;
     if (stages > kMaxStages) stages = kMaxStages;
     pl->n_stages = stages;
@@ -242,7 +244,7 @@ int mpr_create(int device, mpr_handle_t* out) {
         const char* nc = getenv("MPR_NO_CLUSTER");
         if (nc && nc[0] == '1') h->use_cluster = 0;
         const char* ss = getenv("MPR_STAGE_SUBS");
-        if (ss && (ss[0] == '1' || ss[0] == '2')) h->stage_subs = ss[0] - '0';
+        if (ss && (ss[0] == '1' || ss[0] == '2' || ss[0] == '4')) h->stage_subs = ss[0] - '0';
         const char* nq = getenv("MPR_NO_QTMEM");
         if (nq && nq[0] == '1') h->use_q_tmem = 0;
     }

@@ -38,6 +38,7 @@ constexpr int kScanThreads = 320;            // warp 0 TMA, warp 1 MMA, warps 2.
 constexpr int kMaxStages = 12;
 constexpr int kMaxSmem = 232448;              // 227 KiB opt-in limit per CTA on sm_100
 constexpr int kMaxKK = 32;
+constexpr int kMaxSubPerStage = 4;           // 64-wide K sub-chunks per ring stage
 constexpr int kEpiGroups = 2;                 // epilogue groups; group g owns tiles g, g+2, ... (own lists per query)
 constexpr int kCandCapMax = 16;               // per-query pending-candidate slots (a flush leaves >= 8 free)
 
@@ -54,7 +55,7 @@ struct ScanParams {
     int n_splits;
     int n_tiles;       // ceil(n_local / 128)
     int n_stages;
-    int sub_per_stage; // 64-wide K sub-chunks per ring stage (1 or 2): one barrier round-trip per stage
+    int sub_per_stage; // 64-wide K sub-chunks per ring stage (1, 2 or 4): one barrier round-trip per stage
     uint32_t idx_base; // global row index of this shard's row 0
     uint64_t bank_policy;
     const float* bias;     // [n_local]
@@ -236,7 +237,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 ptx::tc_fence_after();
                 if (ptx::elect_one()) {
 #pragma unroll
-                    for (int u = 0; u < 2; ++u) {
+                    for (int u = 0; u < kMaxSubPerStage; ++u) {
                         if (u < ns) {
                             const int j = j0 + u;
                             const uint32_t b_lo = b_lo0 + static_cast<uint32_t>(s * spp + u) * (kStageBytes >> 4);

@@ -92,7 +92,12 @@ def timing(b, n, d, kk, iters=20):
     print(f"timing b={b} n={n} d={d} kk={kk}: {ms*1e3:.1f} us/scan  {n*d*2/ms/1e6:.1f} GB/s  "
           f"{2*b*n*d/ms/1e9:.1f} TFLOP/s  {b/ms*1e3:.0f} q/s plan={pl}", flush=True)
 
-for (b, n, d, kk) in [(16, 1250000, 512, 5), (128, 1250000, 512, 5), (128, 1250000, 512, 16), (128, 1250000, 512, 32),
-                      (256, 1250000, 512, 5), (1024, 1048576, 512, 5), (4096, 1048576, 512, 5), (128, 10000000, 512, 5)]:
+import os
+CASES = [(16, 1250000, 512, 5), (128, 1250000, 512, 5), (256, 1250000, 512, 5), (1024, 1048576, 512, 5),
+         (4096, 1048576, 512, 5), (128, 10000000, 512, 5)]
+if os.environ.get("PROBE_FULL"):
+    CASES += [(128, 1250000, 512, 1), (128, 1250000, 512, 16), (128, 1250000, 512, 32), (16, 1250000, 512, 32),
+              (16, 1000000, 1024, 5), (64, 1000000, 1024, 5), (256, 1000000, 1024, 5), (1, 1250000, 512, 5)]
+for (b, n, d, kk) in CASES:
     timing(b, n, d, kk, iters=10 if b > 256 else 20)
 print("probe done in", time.time() - t0, "s")
