@@ -29,6 +29,7 @@ struct mpr_context {
     int* d_err = nullptr;
     PFN_encodeTiled encode = nullptr;
     std::vector<cudaEvent_t> prof_events;   // start/stop pairs, used only between mpr_profile_begin/end
+    int epi_groups = 2;                     // MPR_EPI_GROUPS=1 forces a single epilogue group
     int stage_subs = 4;                     // max 64-wide K sub-chunks per ring stage (MPR_STAGE_SUBS=1|2|4)
     int use_q_tmem = 1;                     // q-tile as TMEM A operand when D <= 512 (MPR_NO_QTMEM=1 disables)
     int use_cluster = 1;                    // CTA-pair TMA multicast in the tensor-bound regime (MPR_NO_CLUSTER=1 disables)
@@ -60,7 +61,7 @@ static inline int pow2_ceil(int v) { int p = 1; while (p < v) p <<= 1; return p;
 
 // ------------------------------------------------------------------------------------------------ planning
 struct ScanPlan {
-    int n_chunks, q_tile, q_box_rows, n_qtiles, n_splits, n_tiles, n_stages, kk_pad, cand_cap, sub_per_stage;
+    int n_chunks, q_tile, q_box_rows, n_qtiles, n_splits, n_tiles, n_stages, kk_pad, cand_cap, sub_per_stage, n_epi_groups;
     bool q_tmem;       // q-tile in tensor memory (TMEM A operand) instead of shared memory
     uint32_t smem_bytes;
 };
@@ -112,6 +113,9 @@ static int make_plan(mpr_context* h, int b, int64_t n_local, int d, int kk, Scan
     stages /= pl->sub_per_stage;
     if (stages > kMaxStages) stages = kMaxStages;
     pl->n_stages = stages;
+    // two epilogue groups double the epilogue's capacity but split every query's list in two (~1.8x list maintenance);
+    // with <= 32 queries both groups' active warps sit on the same SM sub-partition, so large k gains nothing from it
+    pl->n_epi_groups = (h->epi_groups == 1 || (pl->q_tile <= 32 && pl->kk_pad >= 16)) ? 1 : 2;
     // items = n_splits * n_qtiles should be a whole number of waves over the SMs
     const int g = std::gcd(h->num_sms, pl->n_qtiles);
     pl->n_splits = h->num_sms / g;
@@ -162,6 +166,7 @@ static int launch_scan(mpr_context* h, const ScanPlan& pl, const uint16_t* q, in
     p.n_tiles = pl.n_tiles;
     p.n_stages = pl.n_stages;
     p.sub_per_stage = pl.sub_per_stage;
+    p.n_epi_groups = pl.n_epi_groups;
     p.idx_base = static_cast<uint32_t>(idx_base);
     p.bank_policy = pl.n_qtiles == 1 ? ptx::kEvictFirst : ptx::kEvictNormal;
     p.bias = bias;
@@ -243,6 +248,8 @@ int mpr_create(int device, mpr_handle_t* out) {
     {
         const char* nc = getenv("MPR_NO_CLUSTER");
         if (nc && nc[0] == '1') h->use_cluster = 0;
+        const char* eg = getenv("MPR_EPI_GROUPS");
+        if (eg && eg[0] == '1') h->epi_groups = 1;
         const char* ss = getenv("MPR_STAGE_SUBS");
         if (ss && (ss[0] == '1' || ss[0] == '2' || ss[0] == '4')) h->stage_subs = ss[0] - '0';
         const char* nq = getenv("MPR_NO_QTMEM");

@@ -55,6 +55,7 @@ struct ScanParams {
     int n_splits;
     int n_tiles;       // ceil(n_local / 128)
     int n_stages;
+    int n_epi_groups;  // epilogue groups actually used (1 or 2)
     int sub_per_stage; // 64-wide K sub-chunks per ring stage (1, 2 or 4): one barrier round-trip per stage
     uint32_t idx_base; // global row index of this shard's row 0
     uint64_t bank_policy;
@@ -331,17 +332,21 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             const int r = t * kTileRows + ep_tid;
             return (r < p.n_local) ? __ldg(p.bias + r) : -CUDART_INF_F;   // -inf masks rows past the shard end
         };
-        float next_bias = grp < my_tiles ? load_bias(tile_begin + grp) : 0.f;
+        // With n_epi_groups == 1 group 1 idles: it only writes its (empty) lists.  Used when list maintenance dominates
+        // and both groups' active warps would share one SM sub-partition anyway (few queries, large k).
+        const int n_groups = p.n_epi_groups;
+        const int first_tile = grp < n_groups ? grp : my_tiles;
+        float next_bias = first_tile < my_tiles ? load_bias(tile_begin + first_tile) : 0.f;
 
-        for (int lt = grp; lt < my_tiles; lt += kEpiGroups) {
+        for (int lt = first_tile; lt < my_tiles; lt += n_groups) {
             const int t = tile_begin + lt;
             const int buf = lt & (kBufs - 1);
             const uint32_t bph = (lt / kBufs) & 1u;
             // bias tiles are double-buffered per group: a fast warp may stage tile lt+2 while a slow one still reads lt
-            float* bias_tile = bias_s + (grp * 2 + ((lt >> 1) & 1)) * kTileRows;
+            float* bias_tile = bias_s + (grp * 2 + ((lt / n_groups) & 1)) * kTileRows;
             bias_tile[ep_tid] = next_bias;
             ptx::named_bar_sync(1 + grp, 128);
-            if (lt + kEpiGroups < my_tiles) next_bias = load_bias(t + kEpiGroups);
+            if (lt + n_groups < my_tiles) next_bias = load_bias(t + n_groups);
 
             ptx::mbar_wait(bar_tfull(buf), bph, p.err, kErrTmemFull);
             ptx::tc_fence_after();

@@ -152,3 +152,20 @@ def test_plan_shard_reads_reshards_across_world_sizes():
             assert seen == list(range(n))
     with pytest.raises(ValueError):
         sharding.plan_shard_reads([(0, 10)], 5, 20)
+
+
+def test_header_is_plain_c():
+    """The drop-in boundary must be bindable from C (cgo / JNI / ctypes all consume plain C declarations)."""
+    import shutil
+    import subprocess
+    import tempfile
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    with tempfile.NamedTemporaryFile("w", suffix=".c", delete=False) as f:
+        f.write('#include "%s"\nint main(void) { mpr_handle_t h = 0; (void)h; return MPR_OK; }\n'
+                % os.path.join(ROOT, "include", "mpr_b200.h"))
+    res = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-fsyntax-only", f.name],
+                         capture_output=True, text=True)
+    os.unlink(f.name)
+    assert res.returncode == 0, res.stderr
