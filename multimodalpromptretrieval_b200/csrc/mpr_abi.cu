@@ -29,6 +29,7 @@ struct mpr_context {
     int* d_err = nullptr;
     PFN_encodeTiled encode = nullptr;
     std::vector<cudaEvent_t> prof_events;   // start/stop pairs, used only between mpr_profile_begin/end
+    int cand_cap_override = 0;              // MPR_CAND_CAP=10..16 forces the pending-buffer depth
     int epi_groups = 2;                     // MPR_EPI_GROUPS=1 forces a single epilogue group
     int stage_subs = 4;                     // max 64-wide K sub-chunks per ring stage (MPR_STAGE_SUBS=1|2|4)
     int use_q_tmem = 1;                     // q-tile as TMEM A operand when D <= 512 (MPR_NO_QTMEM=1 disables)
@@ -95,12 +96,35 @@ static int make_plan(mpr_context* h, int b, int64_t n_local, int d, int kk, Scan
             pl->q_box_rows = q_tile_max;
         }
         if (pl->q_tmem) pl->q_box_rows = 0;       // nothing of Q in shared memory
-        for (pl->cand_cap = kCandCapMax; pl->cand_cap >= 10; pl->cand_cap -= 2) {
-            const ScanSmemLayout fixed = scan_smem_layout(pl->n_chunks, pl->q_box_rows, pl->kk_pad, pl->cand_cap, 0, 1);
-            stages = (kMaxSmem - 1024 - static_cast<int>(fixed.total)) / kStageBytes;     // in 16 KiB units
-            if (stages >= 3) break;
+        // List maintenance dominates for k+s >= 16: one epilogue group (one list per query instead of two, ~1.8x less
+        // insert work); otherwise two groups.
+        // The second group's lists must also not starve the bank ring (SS mode keeps 64-128 KiB of Q in shared memory).
+        // (deeper pending buffers were measured to HURT: 32 slots -> +25 % at k+s = 16/32, because the admission
+        // threshold only moves at a flush and a stale threshold admits many more candidates)
+        const int caps1[] = {16, 14, 12, 10, 10}, caps2[] = {16, 14, 12, 10};
+        auto units_for = [&](int cap, int groups) {   // 16 KiB ring units left beside the resident q-tile and the lists
+            const ScanSmemLayout fixed = scan_smem_layout(pl->n_chunks, pl->q_box_rows, pl->kk_pad, cap, 0, 1, groups);
+            return (kMaxSmem - 1024 - static_cast<int>(fixed.total)) / kStageBytes;
+        };
+        pl->n_epi_groups = (h->epi_groups == 1 || pl->kk_pad >= 16 || units_for(16, 2) < 6) ? 1 : 2;
+        const int* caps = pl->n_epi_groups == 1 ? caps1 : caps2;
+        const int n_caps = pl->n_epi_groups == 1 ? 5 : 4;
+        pl->cand_cap = caps[n_caps - 1];
+        stages = units_for(pl->cand_cap, pl->n_epi_groups);
+        for (int want : {6, 3}) {
+            bool found = false;
+            for (int c = 0; c < n_caps && !found; ++c)
+                if (units_for(caps[c], pl->n_epi_groups) >= want) {
+                    pl->cand_cap = caps[c];
+                    stages = units_for(caps[c], pl->n_epi_groups);
+                    found = true;
+                }
+            if (found) break;
         }
-        if (pl->cand_cap < 10) pl->cand_cap = 10;
+        if (h->cand_cap_override >= 10 && h->cand_cap_override <= kCandCapMax && units_for(h->cand_cap_override, pl->n_epi_groups) >= 3) {
+            pl->cand_cap = h->cand_cap_override;      // tuning knob (MPR_CAND_CAP)
+            stages = units_for(pl->cand_cap, pl->n_epi_groups);
+        }
         if (stages >= 3 || q_tile_max <= 32 || pl->q_tmem || pl->q_box_rows < q_tile_max) break;
         q_tile_max >>= 1;
     }
@@ -113,15 +137,12 @@ static int make_plan(mpr_context* h, int b, int64_t n_local, int d, int kk, Scan
     stages /= pl->sub_per_stage;
     if (stages > kMaxStages) stages = kMaxStages;
     pl->n_stages = stages;
-    // two epilogue groups double the epilogue's capacity but split every query's list in two (~1.8x list maintenance);
-    // with <= 32 queries both groups' active warps sit on the same SM sub-partition, so large k gains nothing from it
-    pl->n_epi_groups = (h->epi_groups == 1 || (pl->q_tile <= 32 && pl->kk_pad >= 16)) ? 1 : 2;
     // items = n_splits * n_qtiles should be a whole number of waves over the SMs
     const int g = std::gcd(h->num_sms, pl->n_qtiles);
     pl->n_splits = h->num_sms / g;
     if (pl->n_splits > pl->n_tiles) pl->n_splits = pl->n_tiles;
     if (pl->n_splits < 1) pl->n_splits = 1;
-    pl->smem_bytes = scan_smem_layout(pl->n_chunks, pl->q_box_rows, pl->kk_pad, pl->cand_cap, stages, pl->sub_per_stage).total + 1024u;
+    pl->smem_bytes = scan_smem_layout(pl->n_chunks, pl->q_box_rows, pl->kk_pad, pl->cand_cap, stages, pl->sub_per_stage, pl->n_epi_groups).total + 1024u;
     return MPR_OK;
 }
 
@@ -248,6 +269,8 @@ int mpr_create(int device, mpr_handle_t* out) {
     {
         const char* nc = getenv("MPR_NO_CLUSTER");
         if (nc && nc[0] == '1') h->use_cluster = 0;
+        const char* cc = getenv("MPR_CAND_CAP");
+        if (cc) h->cand_cap_override = atoi(cc);
         const char* eg = getenv("MPR_EPI_GROUPS");
         if (eg && eg[0] == '1') h->epi_groups = 1;
         const char* ss = getenv("MPR_STAGE_SUBS");

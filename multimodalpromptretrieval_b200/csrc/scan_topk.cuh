@@ -78,12 +78,12 @@ __host__ __device__ inline uint32_t scan_row_stride(int kk_pad, int cand_cap) {
 }
 
 __host__ __device__ inline ScanSmemLayout scan_smem_layout(int n_chunks, int q_box_rows, int kk_pad, int cand_cap,
-                                                           int n_stages, int sub_per_stage) {
+                                                           int n_stages, int sub_per_stage, int n_groups) {
     ScanSmemLayout l;
     l.q_off = 0;
     l.stage_off = static_cast<uint32_t>(n_chunks) * q_box_rows * 128u;          // multiple of 1024
     l.list_off = l.stage_off + static_cast<uint32_t>(n_stages) * sub_per_stage * kStageBytes;
-    l.bias_off = l.list_off + static_cast<uint32_t>(kEpiGroups * kUmmaM) * scan_row_stride(kk_pad, cand_cap) * 8u;
+    l.bias_off = l.list_off + static_cast<uint32_t>(n_groups * kUmmaM) * scan_row_stride(kk_pad, cand_cap) * 8u;
     l.bar_off = l.bias_off + kAccBufs * kTileRows * 4u;
     l.total = l.bar_off + (1 + 2 * kMaxStages + 2 * kAccBufs) * 8u + 16u;
     return l;
@@ -112,7 +112,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const uint32_t base = (raw_addr + 1023u) & ~1023u;   // SWIZZLE_128B atoms need 1024-byte alignment
     uint8_t* smem = smem_raw + (base - raw_addr);
 
-    const ScanSmemLayout lay = scan_smem_layout(p.n_chunks, p.q_box_rows, p.kk_pad, p.cand_cap, p.n_stages, p.sub_per_stage);
+    const ScanSmemLayout lay = scan_smem_layout(p.n_chunks, p.q_box_rows, p.kk_pad, p.cand_cap, p.n_stages, p.sub_per_stage, p.n_epi_groups);
     const uint32_t q_smem = base + lay.q_off;
     const uint32_t stage_smem = base + lay.stage_off;
     uint64_t* lists = reinterpret_cast<uint64_t*>(smem + lay.list_off);
@@ -280,7 +280,8 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         const int kk_pad = p.kk_pad;
         uint64_t* my_list = lists + static_cast<size_t>(grp * kUmmaM + row) * scan_row_stride(kk_pad, p.cand_cap);   // [0, kk)
         uint2* my_pend = reinterpret_cast<uint2*>(my_list + kk_pad);                      // (score bits, row)
-        for (int i = 0; i < kk; ++i) my_list[i] = 0ull;
+        const bool active_group = grp < p.n_epi_groups;      // an idle group owns no list memory
+        if (active_group) for (int i = 0; i < kk; ++i) my_list[i] = 0ull;
         float thr = valid ? -CUDART_INF_F : CUDART_INF_F;
         int n_pend = 0;
         const int flush_at = p.cand_cap - 8;           // the next group of 8 scores must always fit
@@ -408,11 +409,11 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         // partial result of this (split, group, q-tile): part_keys[q0 + row][rank][split * 2 + grp] — rank-major per
         // query, so the merge kernel's walk over all lists' rank-i candidates is one contiguous stream
         if (warp_has_work) {
-            flush();
+            if (active_group) flush();
             if (valid) {
                 const size_t n_lists = static_cast<size_t>(p.n_splits) * kEpiGroups;
                 uint64_t* dst = p.part_keys + static_cast<size_t>(q0 + row) * kk * n_lists + split * kEpiGroups + grp;
-                for (int i = 0; i < kk; ++i) dst[static_cast<size_t>(i) * n_lists] = my_list[i];
+                for (int i = 0; i < kk; ++i) dst[static_cast<size_t>(i) * n_lists] = active_group ? my_list[i] : 0ull;
             }
         }
     }
