@@ -12,7 +12,8 @@
 //
 // Work decomposition: item = (bank split s, q-tile t); one CTA per item, blockIdx.x = s * n_qtiles + t, so the
 // CTAs resident at the same time share a bank range and all but the first read of it hit L2.  The q-tile
-// (<= 128 queries, <= 128 KiB) is loaded once and stays resident in shared memory; only the bank streams.
+// (<= 128 queries, <= 128 KiB) is loaded once and stays resident (tensor memory for D <= 512, else shared memory);
+// only the bank streams.
 //
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected lane),
 // warps 2..9 = two epilogue groups of four warps (warp w reads TMEM lanes 32*(w%4)...); group g takes tiles g, g+2, ...
@@ -32,7 +33,7 @@ constexpr int kTileRows = 128;                // bank rows per accumulator tile 
 constexpr int kUmmaM = 128;                   // TMEM lanes = query slots per CTA
 constexpr int kChunkK = 64;                   // bf16 per 128-byte swizzled row
 constexpr int kStageBytes = kTileRows * 128;  // one bank K-chunk: 128 rows x 128 B = 16 KiB
-constexpr int kAccBufs = 4;                   // TMEM accumulator ring: 4 x 128 columns
+constexpr int kAccBufs = 4;                   // TMEM accumulator ring: 4 x 128 columns (2 when the q-tile is in TMEM)
 constexpr int kTmemCols = 512;
 constexpr int kScanThreads = 320;            // warp 0 TMA, warp 1 MMA, warps 2..9 = two epilogue groups of four
 constexpr int kMaxStages = 12;
@@ -48,7 +49,7 @@ struct ScanParams {
     int n_chunks;      // D / 64
     int kk;            // list length (k + skip), 1..32
     int kk_pad;        // next power of two >= kk
-    int cand_cap;      // pending-candidate slots per query (9..16)
+    int cand_cap;      // pending-candidate slots per query (10..16)
     int q_tile;        // queries per q-tile
     int q_box_rows;    // rows of the Q TMA box (multiple of 8, >= valid rows of any q-tile)
     int n_qtiles;
@@ -92,17 +93,17 @@ __host__ __device__ inline ScanSmemLayout scan_smem_layout(int n_chunks, int q_b
 // Barrier error codes (ScanParams::err)
 enum : int { kErrQFull = 101, kErrEmpty = 102, kErrFull = 103, kErrTmemEmpty = 104, kErrTmemFull = 105 };
 
-// kCluster = 2: the two CTAs of a cluster work on the SAME bank split with DIFFERENT q-tiles; each loads half of every
-// bank K-chunk and TMA-multicasts it into both CTAs' rings, halving the L2->SM traffic per MMA (the limiter of the
-// tensor-bound regime with a resident q-tile: 64 B/cycle/SM of bank per 1-CTA MMA cycle vs ~43 B/cycle/SM available).
-// A ring slot is refilled only after BOTH consumers have released it (multicast tcgen05.commit, empty count = 2).
+// kCluster = 2 (shared-memory q-tile variant, even number of q-tiles): the two CTAs of a cluster work on the SAME bank
+// split with DIFFERENT q-tiles; each loads half of every bank K-chunk and TMA-multicasts it into both CTAs' rings, which
+// halves the L2 reads per MMA.  A ring slot is refilled only after BOTH consumers have released it (multicast
+// tcgen05.commit, empty count = 2).  Measured effect at B = 4096: +3 % — L2 bandwidth was not the limiter.
 //
-// kQTmem: the q-tile lives in TENSOR MEMORY instead of shared memory (columns [0, D/2), D <= 512) and is the MMA's
-// TMEM A operand.  With both operands in shared memory a 128x128x16 MMA reads 8 KiB per 64 cycles = the whole
-// 128 B/cycle shared-memory port, so the TMA writes of the next bank chunks and the MMAs throttle each other
-// (measured 41 % tensor-pipe activity at B=4096 with nothing waiting on data).  With A in TMEM only B crosses the port,
-// and the 128 KiB the q-tile used to occupy go to the bank ring (12 stages instead of 4).  The accumulator ring is
-// then 2 x 128 columns at [256, 512).
+// kQTmem (D <= 512): the q-tile lives in TENSOR MEMORY (columns [0, D/2)) and is the MMA's TMEM A operand.  Only B then
+// crosses the 128 B/cycle shared-memory port (an SS-mode 128x128x16 MMA alone reads 8 KiB per 64 cycles = all of it), and
+// the 128 KiB the q-tile used to occupy go to the bank ring (160+ KiB in flight instead of 64).  The accumulator ring is
+// then 2 x 128 columns at [256, 512).  On its own this moved nothing either; what actually bound the tensor regime
+// (41 % tensor-pipe activity with no warp waiting on data) was the MMA warp's own instruction stream — see the
+// warp-uniform issue loop below and the multi-sub-chunk ring stages.
 template <bool kDump, int kCluster, bool kQTmem>
 __global__ void __launch_bounds__(kScanThreads, 1)
 scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_bank,
