@@ -353,7 +353,8 @@ def run_native(args):
                         "ms_per_step region replays a CUDA graph of the same chain"}
 
     if rank == 0:
-        launches_per_step = 4 + (1 if world > 1 else 0)   # bank_build(q), scan, merge, [merge], prompt_gather
+        # [query cast unless fused into the scan (D <= 512)], scan, split merge, [rank merge], prompt gather
+        launches_per_step = (3 if K.search_fused_supported(d, dev.index) else 4) + (1 if world > 1 else 0)
         h2d = q_host.numel() * 4 + int(pre_ids.numel() + pre_off.numel()) * 4
         d2h = int(ids_h.numel() + mask_h.numel()) * 8 + 4
         result = {

@@ -77,6 +77,21 @@ int mpr_search_topk(mpr_handle_t h, const uint16_t* q, int b, const uint16_t* ba
                     int32_t* out_idx, void* workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * Kernel 2 with the query preparation fused in: the raw CLIP outputs src0 [b][d0] (‖ src1 [b][d1])
+ * are concatenated, optionally L2-normalised and rounded to bf16 by the scan kernel itself while it loads the q-tile
+ * into tensor memory — no separate cast launch and no bf16 copy of the queries in HBM.
+ * Replaces: cat([image_encoding, text_encoding], 1).float() + cdist + argsort, dataset/VQAFeatureDataset.py:189-197.
+ * Available when the q-tile lives in tensor memory: 64 <= d0+d1 <= 512 (mpr_search_fused_supported); the reference's
+ * D = 1024 uses mpr_bank_build + mpr_search_topk.  out_q_bias [b] (may be NULL) receives -0.5*||bf16(q)||^2.
+ * With normalise = 0 the results are bit-identical to mpr_bank_build + mpr_search_topk.
+ */
+int mpr_search_fused_supported(mpr_handle_t h, int d);
+int mpr_search_topk_fused(mpr_handle_t h, const void* src0, int d0, const void* src1, int d1, int src_dtype,
+                          int normalise, int b, const uint16_t* bank, const float* bias, int64_t n_local,
+                          int64_t idx_base, int kk, uint64_t* out_keys, float* out_score, int32_t* out_idx,
+                          float* out_q_bias, void* workspace, size_t workspace_bytes, void* stream);
+
+/*
  * Kernel 4 — merge n_lists sorted candidate lists per query: in_keys [n_lists][b][kk] -> top-kk.
  * Used after the NCCL allgather of every rank's out_keys (n_lists = world size).  New in the build: the reference
  * is single-device (main.py:58-61).

@@ -19,6 +19,7 @@ EXPORTS = [
     "mpr_abi_version", "mpr_create", "mpr_destroy", "mpr_last_error", "mpr_device_error", "mpr_bank_build",
     "mpr_search_workspace_bytes", "mpr_search_topk", "mpr_merge_topk", "mpr_prompt_gather", "mpr_debug_scores",
     "mpr_search_plan", "mpr_profile_begin", "mpr_profile_end", "mpr_profile_launch_ms", "mpr_exchange_bytes", "mpr_exchange_push", "mpr_exchange_merge",
+    "mpr_search_fused_supported", "mpr_search_topk_fused",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -68,6 +69,10 @@ def load() -> C.CDLL:
     lib.mpr_profile_begin.argtypes = [vp, i32]
     lib.mpr_profile_end.restype = i32
     lib.mpr_profile_end.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(i32)]
+    lib.mpr_search_fused_supported.restype = i32
+    lib.mpr_search_fused_supported.argtypes = [vp, i32]
+    lib.mpr_search_topk_fused.restype = i32
+    lib.mpr_search_topk_fused.argtypes = [vp, vp, i32, vp, i32, i32, i32, i32, vp, vp, i64, i64, i32, vp, vp, vp, vp, vp, sz, vp]
     lib.mpr_exchange_bytes.restype = sz
     lib.mpr_exchange_bytes.argtypes = [i32, i32]
     lib.mpr_exchange_push.restype = i32

@@ -85,7 +85,8 @@ class RetrievalBank:
                  process_group=None, shard: bool = True, max_source_length: int = 512, name: str = "VQADataset",
                  cache_root: str = "cache", additional_root: str = os.path.join("synthetic_data", "cache",
                                                                                "ROCOFeatureDataset"),
-                 memoise: bool = True, use_cuda_graph: bool = False, exchange: str = "nccl"):
+                 memoise: bool = True, use_cuda_graph: bool = False, exchange: str = "nccl",
+                 fuse_query_cast: bool = True):
         if not torch.cuda.is_available():
             raise RuntimeError("RetrievalBank needs a B200 (sm_100a) GPU; there is no CPU fallback path")
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
@@ -99,6 +100,7 @@ class RetrievalBank:
         self.additional_root = additional_root
         self.memoise = memoise
         self.use_cuda_graph = bool(use_cuda_graph)
+        self.fuse_query_cast = bool(fuse_query_cast)
         if exchange not in ("nccl", "p2p"):
             raise ValueError("exchange must be 'nccl' (all-gather + merge) or 'p2p' (peer-memory push + flag wait)")
         self.exchange_mode = exchange
@@ -327,22 +329,30 @@ class RetrievalBank:
     def search_embeddings(self, image_half: torch.Tensor, text_half: Optional[torch.Tensor] = None, kk: Optional[int] = None
                           ) -> Dict[str, torch.Tensor]:
         """Query halves (device tensors) -> global top-(k+skip): ``score`` fp32 / ``idx`` int32 ``[B, kk]`` and
-        ``q_bias`` fp32 ``[B]`` (= -0.5*|q|^2).  Kernel 1 (queries) -> kernel 2 (+4) -> [all-gather -> kernel 4]."""
+        ``q_bias`` fp32 ``[B]`` (= -0.5*|q|^2).  Kernel 1 (queries; fused into kernel 2 when D <= 512) -> kernel 2 (+4) -> [all-gather -> kernel 4]."""
         if kk is None:
             kk = self.retrieval_k + (1 if self.is_training_phase else 0)
-        q, qbias = K.bank_build(image_half, text_half, normalise=self.normalise)
-        b = q.shape[0]
+        b = image_half.shape[0]
         n_local = self.retrieval_embeddings.shape[0]
+        fused = self.fuse_query_cast and n_local > 0 and K.search_fused_supported(self.dim, self.device.index)
         if n_local > 0:
             need = K.search_workspace_bytes(b, n_local, self.dim, kk, self.device.index)
             if self._workspace is None or self._workspace.numel() < need:
                 self._workspace = torch.empty((max(need, 16),), dtype=torch.uint8, device=self.device)
-            keys, score, idx = K.search_topk(q, self.retrieval_embeddings, self.bias, kk, idx_base=self.row_begin,
-                                             workspace=self._workspace)
+        if fused:
+            # D <= 512: concat + (normalise) + bf16 cast happen inside the scan kernel's q-tile load (N3)
+            keys, score, idx, qbias = K.search_topk_fused(image_half, text_half, self.retrieval_embeddings, self.bias, kk,
+                                                          normalise=self.normalise, idx_base=self.row_begin,
+                                                          workspace=self._workspace)
         else:
-            keys = torch.zeros((b, kk), dtype=torch.int64, device=self.device)
-            score = torch.full((b, kk), float("-inf"), device=self.device)
-            idx = torch.full((b, kk), -1, dtype=torch.int32, device=self.device)
+            q, qbias = K.bank_build(image_half, text_half, normalise=self.normalise)
+            if n_local > 0:
+                keys, score, idx = K.search_topk(q, self.retrieval_embeddings, self.bias, kk, idx_base=self.row_begin,
+                                                 workspace=self._workspace)
+            else:
+                keys = torch.zeros((b, kk), dtype=torch.int64, device=self.device)
+                score = torch.full((b, kk), float("-inf"), device=self.device)
+                idx = torch.full((b, kk), -1, dtype=torch.int32, device=self.device)
         if self.exchange.world_size > 1:
             if self.exchange_mode == "p2p":
                 if self._p2p is None or self._p2p.cap < b * kk:

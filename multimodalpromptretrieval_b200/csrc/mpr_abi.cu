@@ -161,12 +161,21 @@ static int encode_2d(mpr_context* h, CUtensorMap* map, const void* ptr, uint64_t
     return MPR_OK;
 }
 
+struct FusedQ {            // raw query halves for the fused-cast variant (src0 == nullptr: q is already bf16)
+    const void* src0 = nullptr;
+    const void* src1 = nullptr;
+    int d0 = 0, d1 = 0, dtype = 0, normalise = 0;
+    float* q_bias_out = nullptr;
+};
+
 template <bool kDump>
 static int launch_scan(mpr_context* h, const ScanPlan& pl, const uint16_t* q, int b, const uint16_t* bank,
                        const float* bias, int64_t n_local, int64_t idx_base, int d, int kk, uint64_t* part_keys,
-                       float* dump, cudaStream_t st) {
+                       float* dump, cudaStream_t st, const FusedQ& fq = FusedQ()) {
     CUtensorMap tq, tb;
-    int rc = encode_2d(h, &tq, q, static_cast<uint64_t>(b), static_cast<uint64_t>(d), pl.q_tmem ? 8 : pl.q_box_rows);
+    int rc = MPR_OK;
+    if (pl.q_tmem) memset(&tq, 0, sizeof(tq));       // the TMEM variant never touches the Q tensor map
+    else rc = encode_2d(h, &tq, q, static_cast<uint64_t>(b), static_cast<uint64_t>(d), pl.q_box_rows);
     if (rc) return rc;
     // tensor-bound regime with an even number of q-tiles: CTA pairs share each bank chunk by TMA multicast
     const bool pair = !kDump && !pl.q_tmem && h->use_cluster && pl.n_qtiles >= 2 && pl.n_qtiles % 2 == 0;
@@ -193,6 +202,13 @@ static int launch_scan(mpr_context* h, const ScanPlan& pl, const uint16_t* q, in
     p.bias = bias;
     p.q = q;
     p.d = d;
+    p.qsrc0 = fq.src0;
+    p.qsrc1 = fq.src1;
+    p.qd0 = fq.d0;
+    p.qd1 = fq.d1;
+    p.q_dtype = fq.dtype;
+    p.q_normalise = fq.normalise;
+    p.q_bias_out = fq.q_bias_out;
     p.part_keys = part_keys;
     p.dump = dump;
     p.err = h->d_err;
@@ -214,6 +230,8 @@ static int launch_scan(mpr_context* h, const ScanPlan& pl, const uint16_t* q, in
         cfg.attrs = attr;
         cfg.numAttrs = 1;
         CUDA_TRY(h, cudaLaunchKernelEx(&cfg, scan_topk_kernel<false, 2, false>, tq, tb, p));
+    } else if (pl.q_tmem && fq.src0) {
+        scan_topk_kernel<false, 1, true, true><<<grid, kScanThreads, pl.smem_bytes, st>>>(tq, tb, p);
     } else if (pl.q_tmem) {
         scan_topk_kernel<kDump, 1, true><<<grid, kScanThreads, pl.smem_bytes, st>>>(tq, tb, p);
     } else {
@@ -266,6 +284,8 @@ int mpr_create(int device, mpr_handle_t* out) {
         e = cudaFuncSetAttribute(scan_topk_kernel<false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(scan_topk_kernel<true, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(scan_topk_kernel<false, 1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     {
         const char* nc = getenv("MPR_NO_CLUSTER");
         if (nc && nc[0] == '1') h->use_cluster = 0;
@@ -398,6 +418,44 @@ int mpr_search_topk(mpr_handle_t h, const uint16_t* q, int b, const uint16_t* ba
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     uint64_t* part = static_cast<uint64_t*>(workspace);
     rc = launch_scan<false>(h, pl, q, b, bank, bias, n_local, idx_base, d, kk, part, nullptr, st);
+    if (rc) return rc;
+    const int warps_per_block = 4;
+    merge_topk_kernel<<<(b + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(
+        part, pl.n_splits * kEpiGroups, 1ll, static_cast<long long>(kk) * pl.n_splits * kEpiGroups,
+        static_cast<long long>(pl.n_splits) * kEpiGroups, b, kk, out_keys, out_score, out_idx);
+    CUDA_TRY(h, cudaGetLastError());
+    return MPR_OK;
+}
+
+int mpr_search_fused_supported(mpr_handle_t h, int d) { return h && h->use_q_tmem && d >= 64 && d <= 512 && d % 64 == 0; }
+
+int mpr_search_topk_fused(mpr_handle_t h, const void* src0, int d0, const void* src1, int d1, int src_dtype,
+                          int normalise, int b, const uint16_t* bank, const float* bias, int64_t n_local,
+                          int64_t idx_base, int kk, uint64_t* out_keys, float* out_score, int32_t* out_idx,
+                          float* out_q_bias, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!h) return fail(nullptr, MPR_EINVAL, "null handle");
+    if (b == 0) return MPR_OK;
+    if (!src1) d1 = 0;
+    const int d = d0 + d1;
+    if (!src0 || !bank || !bias || !workspace) return fail(h, MPR_EINVAL, "null pointer");
+    if (d0 < 8 || d0 % 8 || d1 % 8) return fail(h, MPR_EINVAL, "query halves must be multiples of 8 wide (d0=%d d1=%d)", d0, d1);
+    if (!mpr_search_fused_supported(h, d))
+        return fail(h, MPR_EINVAL, "fused query preparation needs the tensor-memory q-tile (64 <= D <= 512, D %% 64 == 0); got D=%d", d);
+    if (src_dtype < MPR_SRC_F32 || src_dtype > MPR_SRC_BF16) return fail(h, MPR_EINVAL, "bad src_dtype %d", src_dtype);
+    if (!aligned16(src0) || !aligned16(src1) || !aligned16(bank) || !aligned16(workspace))
+        return fail(h, MPR_EINVAL, "pointers must be 16-byte aligned");
+    if (idx_base < 0 || idx_base + n_local >= 0xFFFFFFFFll) return fail(h, MPR_EINVAL, "global row index exceeds 32 bits");
+    ScanPlan pl;
+    int rc = make_plan(h, b, n_local, d, kk, &pl);
+    if (rc) return rc;
+    const size_t need = static_cast<size_t>(pl.n_splits) * kEpiGroups * b * kk * sizeof(uint64_t);
+    if (workspace_bytes < need) return fail(h, MPR_EWORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, need);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    uint64_t* part = static_cast<uint64_t*>(workspace);
+    FusedQ fq;
+    fq.src0 = src0; fq.src1 = src1; fq.d0 = d0; fq.d1 = d1; fq.dtype = src_dtype; fq.normalise = normalise;
+    fq.q_bias_out = out_q_bias;
+    rc = launch_scan<false>(h, pl, nullptr, b, bank, bias, n_local, idx_base, d, kk, part, nullptr, st, fq);
     if (rc) return rc;
     const int warps_per_block = 4;
     merge_topk_kernel<<<(b + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(

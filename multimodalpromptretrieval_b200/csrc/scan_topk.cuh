@@ -24,6 +24,7 @@
 #include <cstdint>
 #include <math_constants.h>
 
+#include "bank_build.cuh"
 #include "ptx.cuh"
 #include "topk_key.cuh"
 
@@ -63,6 +64,12 @@ struct ScanParams {
     const float* bias;     // [n_local]
     const uint16_t* q;     // [b_total][d] bf16 queries (read directly in the TMEM-operand variant)
     int d;                 // row length
+    // fused query preparation (kFuseQ): the raw CLIP halves are concatenated, optionally normalised and rounded to bf16
+    // on their way into tensor memory — no separate cast kernel, no bf16 copy of the queries in HBM
+    const void* qsrc0;     // [b_total][qd0]
+    const void* qsrc1;     // [b_total][qd1] or nullptr
+    int qd0, qd1, q_dtype, q_normalise;
+    float* q_bias_out;     // [b_total] -0.5*|bf16(q)|^2 (written by split 0), or nullptr
     uint64_t* part_keys;   // [b_total][kk][n_splits * kEpiGroups]
     float* dump;           // debug: [b_total][n_local] scores, or nullptr
     int* err;              // device word that receives the code of a starved barrier
@@ -104,7 +111,8 @@ enum : int { kErrQFull = 101, kErrEmpty = 102, kErrFull = 103, kErrTmemEmpty = 1
 // then 2 x 128 columns at [256, 512).  On its own this moved nothing either; what actually bound the tensor regime
 // (41 % tensor-pipe activity with no warp waiting on data) was the MMA warp's own instruction stream — see the
 // warp-uniform issue loop below and the multi-sub-chunk ring stages.
-template <bool kDump, int kCluster, bool kQTmem>
+// kFuseQ (with kQTmem): see ScanParams::qsrc0 — replaces /root/reference/dataset/VQAFeatureDataset.py:189-191 in-kernel.
+template <bool kDump, int kCluster, bool kQTmem, bool kFuseQ = false>
 __global__ void __launch_bounds__(kScanThreads, 1)
 scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_bank,
                  const ScanParams p) {
@@ -313,16 +321,56 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         if (kQTmem && grp == 0) {
             // This thread's query row -> its TMEM lane, columns [0, D/2): 8 bf16 (one uint4) fill 4 columns.
             const uint32_t q_taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
-            const uint4* qrow = reinterpret_cast<const uint4*>(p.q + static_cast<size_t>(valid ? q0 + row : 0) * p.d);
-            for (int c0 = 0; c0 < p.d / 2; c0 += 32) {
-                uint32_t w[32];
+            const size_t qrow_idx = static_cast<size_t>(valid ? q0 + row : 0);
+            if constexpr (kFuseQ) {
+                auto load_q8 = [&](int col, float (&x)[8]) {      // 8 consecutive elements of [src0 | src1]
+                    if (col < p.qd0) load8(p.qsrc0, p.q_dtype, qrow_idx * p.qd0 + col, x);
+                    else             load8(p.qsrc1, p.q_dtype, qrow_idx * p.qd1 + (col - p.qd0), x);
+                };
+                float scale = 1.f;
+                if (p.q_normalise && valid) {
+                    float ss = 0.f;
+                    for (int col = 0; col < p.d; col += 8) {
+                        float x[8];
+                        load_q8(col, x);
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    uint4 t = make_uint4(0u, 0u, 0u, 0u);
-                    if (valid) t = __ldg(qrow + c0 / 4 + u);
-                    w[4 * u + 0] = t.x; w[4 * u + 1] = t.y; w[4 * u + 2] = t.z; w[4 * u + 3] = t.w;
+                        for (int i = 0; i < 8; ++i) ss = fmaf(x[i], x[i], ss);
+                    }
+                    scale = ss > 0.f ? 1.0f / sqrtf(ss) : 0.f;
                 }
-                ptx::tmem_st_32x32b_x32(q_taddr + c0, w);
+                float rs = 0.f;
+                for (int c0 = 0; c0 < p.d / 2; c0 += 32) {
+                    uint32_t w[32];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        float x[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                        if (valid) load_q8(c0 * 2 + u * 8, x);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const __nv_bfloat16 lo = __float2bfloat16_rn(x[2 * i] * scale);
+                            const __nv_bfloat16 hi = __float2bfloat16_rn(x[2 * i + 1] * scale);
+                            const float flo = __bfloat162float(lo), fhi = __bfloat162float(hi);
+                            rs = fmaf(flo, flo, rs);
+                            rs = fmaf(fhi, fhi, rs);
+                            w[4 * u + i] = static_cast<uint32_t>(__bfloat16_as_ushort(lo)) |
+                                           (static_cast<uint32_t>(__bfloat16_as_ushort(hi)) << 16);
+                        }
+                    }
+                    ptx::tmem_st_32x32b_x32(q_taddr + c0, w);
+                }
+                if (valid && split == 0 && p.q_bias_out) p.q_bias_out[q0 + row] = -0.5f * rs;
+            } else {
+                const uint4* qrow = reinterpret_cast<const uint4*>(p.q + qrow_idx * p.d);
+                for (int c0 = 0; c0 < p.d / 2; c0 += 32) {
+                    uint32_t w[32];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        uint4 t = make_uint4(0u, 0u, 0u, 0u);
+                        if (valid) t = __ldg(qrow + c0 / 4 + u);
+                        w[4 * u + 0] = t.x; w[4 * u + 1] = t.y; w[4 * u + 2] = t.z; w[4 * u + 3] = t.w;
+                    }
+                    ptx::tmem_st_32x32b_x32(q_taddr + c0, w);
+                }
             }
             ptx::tmem_wait_st();
             ptx::tc_fence_before();

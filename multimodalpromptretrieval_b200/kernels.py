@@ -104,6 +104,42 @@ def search_topk(q: torch.Tensor, bank: torch.Tensor, bias: torch.Tensor, kk: int
     return out_keys, out_score, out_idx
 
 
+def search_fused_supported(d: int, device: Optional[int] = None) -> bool:
+    h = handle(device)
+    return bool(h.lib.mpr_search_fused_supported(h.ptr, int(d)))
+
+
+def search_topk_fused(src0: torch.Tensor, src1: Optional[torch.Tensor], bank: torch.Tensor, bias: torch.Tensor, kk: int,
+                      normalise: bool = False, idx_base: int = 0, workspace: Optional[torch.Tensor] = None
+                      ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Kernel 2 with the query concat / normalise / bf16 cast fused into its q-tile load (D <= 512).
+    Returns (keys, score, idx, q_bias)."""
+    h = handle(src0.device.index)
+    assert src0.is_cuda and src0.dim() == 2 and src0.is_contiguous() and bank.dtype == torch.bfloat16
+    b, d0 = src0.shape
+    d1 = 0
+    if src1 is not None:
+        assert src1.is_contiguous() and src1.shape[0] == b and src1.dtype == src0.dtype
+        d1 = src1.shape[1]
+    d = d0 + d1
+    n_local = bank.shape[0]
+    assert bank.shape[1] == d and bias.shape[0] == n_local
+    dev = src0.device
+    out_keys = torch.empty((b, kk), dtype=torch.int64, device=dev)
+    out_score = torch.empty((b, kk), dtype=torch.float32, device=dev)
+    out_idx = torch.empty((b, kk), dtype=torch.int32, device=dev)
+    q_bias = torch.empty((b,), dtype=torch.float32, device=dev)
+    need = search_workspace_bytes(b, n_local, d, kk, dev.index)
+    if workspace is None or workspace.numel() * workspace.element_size() < need:
+        workspace = torch.empty((max(need, 16),), dtype=torch.uint8, device=dev)
+    rc = h.lib.mpr_search_topk_fused(h.ptr, _ptr(src0), d0, _ptr(src1), d1, _DTYPES[src0.dtype], int(bool(normalise)), b,
+                                     _ptr(bank), _ptr(bias), n_local, idx_base, kk, _ptr(out_keys), _ptr(out_score),
+                                     _ptr(out_idx), _ptr(q_bias), _ptr(workspace),
+                                     workspace.numel() * workspace.element_size(), _stream())
+    h.check(rc, "mpr_search_topk_fused")
+    return out_keys, out_score, out_idx, q_bias
+
+
 def merge_topk(keys: torch.Tensor, out_keys: Optional[torch.Tensor] = None, out_score: Optional[torch.Tensor] = None,
                out_idx: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """Kernel 4: ``keys [n_lists, b, kk]`` (each list sorted) → global top-kk."""

@@ -469,3 +469,37 @@ def test_shard_cache_roundtrip_and_resharding(tmp_path, golden_cases, tokenizer)
         assert part.load_shards(str(tmp_path / "shards"), key)
         b0, b1 = part.row_begin, part.row_begin + part.retrieval_embeddings.shape[0]
         assert torch.equal(part.retrieval_embeddings, src.retrieval_embeddings[b0:b1])
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+@pytest.mark.parametrize("b,d0,d1,kk", [(16, 256, 256, 5), (128, 512, 0, 1), (130, 64, 64, 6), (300, 256, 0, 16)])
+def test_fused_query_cast_is_bit_identical_to_two_step(K, dtype, b, d0, d1, kk):
+    """N3: concat + bf16 cast of the raw query halves inside the scan kernel's q-tile load == kernel 1 + kernel 2."""
+    n, d = 20011, d0 + d1
+    assert K.search_fused_supported(d) and not K.search_fused_supported(1024)
+    bank = clip_like(n, d, 3).to(dev())
+    _, bias = K.bank_build(bank)
+    g = torch.Generator().manual_seed(b)
+    a = (torch.randn(b, d0, generator=g) * 0.44).to(dtype).to(dev())
+    t = (torch.randn(b, d1, generator=g) * 0.44).to(dtype).to(dev()) if d1 else None
+    q, qbias = K.bank_build(a, t)
+    keys_ref, score_ref, idx_ref = K.search_topk(q, bank, bias, kk, idx_base=7)
+    keys, score, idx, qb = K.search_topk_fused(a, t, bank, bias, kk, idx_base=7)
+    assert torch.equal(keys, keys_ref) and torch.equal(idx, idx_ref) and torch.equal(score, score_ref)
+    assert (qb - qbias).abs().max().item() < 1e-3
+    assert K.handle(0).device_error() == 0
+
+
+def test_fused_query_cast_with_normalise(K):
+    n, d, b, kk = 30000, 512, 64, 5
+    g = torch.Generator().manual_seed(9)
+    src = torch.randn(n, d, generator=g).to(dev())
+    bank, bias = K.bank_build(src, normalise=True)
+    qsrc = (src[:b] + 0.05 * torch.randn(b, d, generator=g).to(dev())).contiguous()
+    q, _ = K.bank_build(qsrc, normalise=True)
+    _, score_ref, idx_ref = K.search_topk(q, bank, bias, kk)
+    _, score, idx, qb = K.search_topk_fused(qsrc, None, bank, bias, kk, normalise=True)
+    assert (idx[:, 0] == torch.arange(b, device=dev())).all()           # each query's own row is its nearest
+    assert (score - score_ref).abs().max().item() < 2e-3                # norm summation order: <= 1 bf16 ulp on few elements
+    assert (idx == idx_ref).float().mean().item() > 0.98
+    assert (qb + 0.5).abs().max().item() < 5e-3
