@@ -390,8 +390,26 @@ def run_native(args):
     os._exit(0)
 
 
+def relaunch_under_torchrun(args) -> None:
+    """`python bench.py --gpus N` (N > 1) without a launcher: start one rank per GPU ourselves, exactly as the driver
+    would (`python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ...`)."""
+    import socket
+    with socket.socket() as sock:
+        sock.bind(("127.0.0.1", 0))
+        port = sock.getsockname()[1]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
+    if os.environ.get("MPR_BENCH_DRY_RUN"):
+        print(" ".join(cmd))
+        return
+    os.execv(sys.executable, cmd)
+
+
 def main():
     args = parse_args()
+    if args.gpus > 1 and "RANK" not in os.environ and args.impl == "native":
+        relaunch_under_torchrun(args)
+        return
     # hard stop: a benchmark must not hang a GPU box (or the driver's scaling run) under any circumstances
     watchdog = threading.Timer(args.max_seconds, lambda: (sys.stderr.write("bench watchdog expired\n"), os._exit(124)))
     watchdog.daemon = True

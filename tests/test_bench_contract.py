@@ -30,3 +30,14 @@ def test_reference_arm_other_ranks_exit_quietly():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
                           "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_multi_gpu_request_without_launcher_starts_torchrun():
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    env["MPR_BENCH_DRY_RUN"] = "1"
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--gpus", "4", "--steps", "7"],
+                         capture_output=True, text=True, timeout=60, cwd=ROOT, env=env)
+    assert out.returncode == 0
+    cmd = out.stdout.strip()
+    assert "torch.distributed.run" in cmd and "--nproc-per-node=4" in cmd and "--master-addr 127.0.0.1" in cmd
+    assert cmd.endswith("--gpus 4 --steps 7")
