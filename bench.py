@@ -195,8 +195,11 @@ def run_native(args):
     dev = torch.device(f"cuda:{local_rank}")
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"      # NCCL's version banner goes to stdout; keep stdout = one JSON line
+        # stdout must stay ONE JSON line: NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION/WARN (the image
+        # sets one of them); drop those levels and send anything an explicit INFO/TRACE asks for to stderr
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+            del os.environ["NCCL_DEBUG"]
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     from multimodalpromptretrieval_b200 import kernels as K
