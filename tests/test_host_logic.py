@@ -169,3 +169,18 @@ def test_header_is_plain_c():
                          capture_output=True, text=True)
     os.unlink(f.name)
     assert res.returncode == 0, res.stderr
+
+
+def test_word_cached_tokenisation_equals_direct_tokenisation(tokenizer):
+    """encode_by_words (per-chunk cache) == the tokenizer on the whole string, cold and warm, incl. odd whitespace,
+    punctuation-only chunks and non-ASCII text (which must take the direct path)."""
+    from multimodalpromptretrieval_b200 import synthetic as S
+    tables = prompt.PromptTables(tokenizer, ["yes"], torch.device("cpu"))
+    texts = [f"{q} #{i}-{i * 7}I" for i, q in enumerate(S.make_questions(300, 21))]
+    texts += ["", "I", " lead spaceThe", "trail I", "a\\tb cI", "x\\ny", "A  B   C", "a--b ?! ::", "1/2 ½ thingsI",
+              "é accentI", "nb\\xa0spI", "ｆｕｌｌwidth textI", "  ", "what is   the  organ  ?I"]
+    ref = tokenizer(texts, add_special_tokens=False)["input_ids"]
+    assert tables.encode_by_words(texts) == ref                  # cold cache
+    assert tables.encode_by_words(texts) == ref                  # warm cache
+    assert tables.encode_by_words(list(reversed(texts))) == list(reversed(ref))
+    assert all(w.isascii() and " " not in w for w in tables._word_cache)
