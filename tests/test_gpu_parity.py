@@ -100,6 +100,7 @@ TOPK_CASES = [
     (128, 20000, 512, 5), (129, 20000, 512, 5), (300, 30000, 512, 16), (64, 2000, 1024, 15), (65, 2000, 1024, 16),
     (7, 127, 64, 3), (7, 128, 64, 3), (7, 129, 64, 3), (3, 1, 64, 1), (40, 50000, 256, 31),
     (512, 60000, 512, 5), (256, 4000, 1024, 3), (1000, 9000, 512, 2),     # even q-tile counts: CTA-pair multicast path
+    (4, 3, 64, 5), (9, 20, 1024, 32),                                     # k > N: fewer rows than list slots
 ]
 
 
