@@ -40,6 +40,40 @@ N_ANSWERS = 24           # ROCO synthetic-QA answer vocabulary
 CPU_SAMPLE_ROWS = 250_000
 
 
+def host_threads() -> int:
+    """All host cores this process may use.  torchrun exports OMP_NUM_THREADS=1, which would silently turn the CPU arm
+    into a one-thread run (round-1 SCALE lines): size torch's pool from the affinity mask instead and say how many."""
+    import torch
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    torch.set_num_threads(max(1, n))
+    return torch.get_num_threads()
+
+
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout, but libraries print to fd 1 as well (NCCL's banner at
+    NCCL_DEBUG=VERSION).  fd 1 is pointed at stderr for the run and the result line goes to the saved original, so
+    nobody's logging has to be edited."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        _JSON_OUT = os.fdopen(saved, "w")
+    return _JSON_OUT
+
+
+def emit(result: dict) -> None:
+    out = claim_stdout()
+    out.write(json.dumps(result) + "\n")
+    out.flush()
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -116,7 +150,7 @@ def run_reference_arm(args, rank: int, n_gpus: int):
         return
     import torch
     from oracle import retrieval_oracle as O
-    threads = torch.get_num_threads()
+    threads = host_threads()
     sample_rows = min(CPU_SAMPLE_ROWS, args.bank_rows)
     g = torch.Generator().manual_seed(88)
     bank = torch.randn(sample_rows, args.dim, generator=g) * (10.0 / args.dim ** 0.5)
@@ -155,14 +189,14 @@ def run_reference_arm(args, rank: int, n_gpus: int):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "host": {"cpu_count": os.cpu_count(), "torch_threads": threads},
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 def cpu_baseline(args):
     """Bounded CPU sample next to the GPU number (rank 0, N = 1): ~10-30 s of host work."""
     import torch
     from oracle import retrieval_oracle as O
-    threads = torch.get_num_threads()
+    threads = host_threads()
     rows = min(CPU_SAMPLE_ROWS, args.bank_rows)
     g = torch.Generator().manual_seed(88)
     bank = torch.randn(rows, args.dim, generator=g) * (10.0 / args.dim ** 0.5)
@@ -195,11 +229,6 @@ def run_native(args):
     dev = torch.device(f"cuda:{local_rank}")
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # stdout must stay ONE JSON line: NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION/WARN (the image
-        # sets one of them); drop those levels and send anything an explicit INFO/TRACE asks for to stderr
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
-            del os.environ["NCCL_DEBUG"]
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     from multimodalpromptretrieval_b200 import kernels as K
@@ -380,10 +409,10 @@ def run_native(args):
         }
         if n_gpus == 1 and not args.no_cpu_baseline:
             result["cpu_baseline"] = cpu_baseline(args)
-        print(json.dumps(result), flush=True)
-    # Teardown: CUDA graphs that captured NCCL kernels must go before the communicator does, and a hung
-    # communicator teardown must never keep the launcher alive — leave through os._exit once every rank is done.
-    sys.stdout.flush()
+        emit(result)
+    # Teardown in dependency order, then a NORMAL interpreter exit (atexit hooks and the driver's loaded-library record
+    # run): graphs that captured collective kernels go before the communicator does.  The result line is already out;
+    # if a communicator teardown ever hangs, a short timer ends the process with status 0 instead of stalling the launcher.
     if not args.no_graph:
         graph_out.clear()
         graph.reset()
@@ -392,7 +421,10 @@ def run_native(args):
     if world > 1:
         dist.barrier()
         torch.cuda.synchronize()
-    os._exit(0)
+        guard = threading.Timer(60.0, lambda: os._exit(0))
+        guard.daemon = True
+        guard.start()
+        dist.destroy_process_group()
 
 
 def relaunch_under_torchrun(args) -> None:
