@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define MPR_ABI_VERSION 1
+#define MPR_ABI_VERSION 2
 
 enum {
     MPR_OK = 0,
@@ -79,10 +79,11 @@ int mpr_search_topk(mpr_handle_t h, const uint16_t* q, int b, const uint16_t* ba
 /*
  * Kernel 2 with the query preparation fused in: the raw CLIP outputs src0 [b][d0] (‖ src1 [b][d1])
  * are concatenated, optionally L2-normalised and rounded to bf16 by the scan kernel itself while it loads the q-tile
- * into tensor memory — no separate cast launch and no bf16 copy of the queries in HBM.
+ * (tensor or shared memory) — no separate cast launch and no bf16 copy of the queries in HBM.
  * Replaces: cat([image_encoding, text_encoding], 1).float() + cdist + argsort, dataset/VQAFeatureDataset.py:189-197.
- * Available when the q-tile lives in tensor memory: 64 <= d0+d1 <= 512 (mpr_search_fused_supported); the reference's
- * D = 1024 uses mpr_bank_build + mpr_search_topk.  out_q_bias [b] (may be NULL) receives -0.5*||bf16(q)||^2.
+ * Available for 64 <= d0+d1 <= 2048 (mpr_search_fused_supported): D <= 512 keeps the q-tile in tensor memory (each
+ * epilogue thread converts its own row), larger D — the reference's 1024 — fills the shared-memory q-tile a warp per
+ * row.  out_q_bias [b] (may be NULL) receives -0.5*||bf16(q)||^2.
  * With normalise = 0 the results are bit-identical to mpr_bank_build + mpr_search_topk.
  */
 int mpr_search_fused_supported(mpr_handle_t h, int d);
@@ -100,20 +101,14 @@ int mpr_merge_topk(mpr_handle_t h, const uint64_t* in_keys, int n_lists, int b, 
                    float* out_score, int32_t* out_idx, void* stream);
 
 /*
- * Candidate exchange over NVLink peer memory (alternative to NCCL all-gather + mpr_merge_topk on one NVSwitch box;
- * csrc/exchange.cuh).  Every rank allocates one buffer of mpr_exchange_bytes(world, cap) bytes that is mapped into all
- * peers (symmetric memory), zero-filled before first use.  peer_bufs is a HOST array of `world` device pointers, entry r
- * = rank r's buffer as addressable from this device (entry `rank` = the local buffer).  cap >= b*kk.
- *   mpr_exchange_push : store this rank's [b][kk] keys into every rank's buffer and raise the delivery flags.
- *   mpr_exchange_merge: wait for all `world` deliveries, merge them (score desc, row asc) into the global top-kk.
- * Both are single launches on `stream`, keep their epoch in device memory and are CUDA-graph capturable.  New in the
- * build: the reference is single-device (main.py:58-61).
+ * Candidate exchange over NVLink peer memory (one NVSwitch box).  Every rank allocates one buffer of
+ * mpr_exchange_bytes(world, cap) bytes that is mapped into all peers (symmetric memory), zero-filled before first use;
+ * cap >= b*kk of any search that will use it.  The exchange itself runs inside mpr_retrieve (see there): per query, the
+ * rank's merged local top-kk is stored into every peer's buffer (plain P2P stores + a release flag), the peers'
+ * deliveries of the same query are awaited and the `world` lists merged in rank order.  New in the build: the reference
+ * is single-device (main.py:58-61).
  */
 size_t mpr_exchange_bytes(int world, int cap);
-int mpr_exchange_push(mpr_handle_t h, const uint64_t* local_keys, int b, int kk, int rank, int world,
-                      void* const* peer_bufs, int cap, void* stream);
-int mpr_exchange_merge(mpr_handle_t h, void* my_buf, int world, int cap, int b, int kk, uint64_t* out_keys,
-                       float* out_score, int32_t* out_idx, void* stream);
 
 /*
  * Kernel 3 — retrieved rows -> answers -> majority vote -> quantifier bucket -> prompt token ids.
@@ -132,6 +127,126 @@ int mpr_prompt_gather(mpr_handle_t h, const int32_t* idx, int b, int kk, int ski
                       int32_t* maj_answer, int32_t* maj_count, int32_t* bucket, int32_t* ret_answer, void* stream);
 
 /*
+ * One retrieval step, device side — the call RetrievalBank.retrieve_closest_qa_pairs / retrieve_prompt_ids make:
+ *   query preparation (cat + optional normalise + bf16 round; dataset/VQAFeatureDataset.py:189-191)
+ *   -> bank scan with fused streaming top-(k+skip)  (torch.cdist + torch.argsort[:, s:s+k]; :192-197)
+ *   -> merge of the per-CTA partial lists
+ *   -> [world > 1] peer-memory exchange of the [b][kk] candidates and merge in rank order
+ *   -> [answer_id != NULL] answers of the retrieved rows, majority vote, quantifier bucket, prompt token ids
+ *      (:199,215-230 and the tokenizer call of architectures/T5VisionModel.py:153-167)
+ * When the scan grid is a single wave (b <= 512 or so) ALL of this is ONE cooperative kernel launch: after a grid
+ * barrier the scan kernel's warps finish whole queries.  Larger batches use two launches (scan, tail).
+ *
+ * Queries: either raw halves q0 [b][d0] (|| q1 [b][d1]) of q_dtype (MPR_SRC_*) — prepared inside the scan kernel — or
+ * q_bf16 [b][d] prepared earlier by mpr_bank_build (q0 == NULL).  q_scratch [b][d] bf16 is only needed for raw queries
+ * with d > 512 and b > 128 (the kernel variant that shares bank tiles between CTA pairs takes prepared queries).
+ * All pointers are device pointers owned by the caller; outputs may be NULL where noted.  The workspace
+ * (mpr_search_workspace_bytes) belongs to ONE stream at a time; its control words are (re)zeroed by the library.
+ * Sharded search (world > 1) is a COLLECTIVE: every rank must issue the same sequence of calls.
+ */
+typedef struct mpr_retrieve_args {
+    /* queries */
+    const void* q0;            /* raw image half [b][d0], or NULL */
+    const void* q1;            /* raw text half [b][d1], or NULL  */
+    int d0, d1, q_dtype, normalise;
+    const uint16_t* q_bf16;    /* prepared queries [b][d] (used when q0 == NULL) */
+    uint16_t* q_scratch;       /* [b][d] bf16 or NULL, see above */
+    int b;
+    /* this rank's bank shard */
+    const uint16_t* bank;      /* [n_local][d] bf16 row-major */
+    const float* bias;         /* [n_local] = -0.5*|row|^2    */
+    int64_t n_local, idx_base;
+    int d, kk;                 /* kk = k + skip               */
+    /* search results (each may be NULL) */
+    uint64_t* out_keys;        /* [b][kk] sortable candidates  */
+    float* out_score;          /* [b][kk]                      */
+    int32_t* out_idx;          /* [b][kk] global rows, -1 none */
+    float* out_q_bias;         /* [b] -0.5*|bf16(q)|^2 (raw queries only) */
+    void* workspace;
+    size_t workspace_bytes;
+    /* multi-GPU exchange: world <= 1 disables it */
+    int rank, world, xchg_cap;
+    void* const* peer_bufs;    /* HOST array of `world` device pointers (entry `rank` = the local buffer) */
+    /* prompt stage: answer_id == NULL disables it */
+    int skip;
+    const int32_t* answer_id;
+    const uint8_t* bucket_lut;
+    const int32_t* prefix_ids;
+    const int32_t* prefix_off;
+    const int32_t* seg_ids;
+    const int32_t* seg_off;
+    int use_quantifier, pad_id, eos_id, max_len, out_stride;
+    int64_t* input_ids;        /* [b][out_stride] */
+    int64_t* attention_mask;   /* [b][out_stride] */
+    int32_t* out_len;          /* [b] */
+    int32_t* maj_answer;       /* [b] */
+    int32_t* maj_count;        /* [b] */
+    int32_t* bucket;           /* [b] */
+    int32_t* ret_answer;       /* [b][k] or NULL */
+    int32_t* status;           /* device word, 0 = ok, MPR_STATUS_* otherwise (may be NULL) */
+} mpr_retrieve_args;
+
+#define MPR_STATUS_XCHG_TIMEOUT 201 /* a peer rank did not deliver its candidates in time; local results returned */
+
+int mpr_retrieve(mpr_handle_t h, const mpr_retrieve_args* a, void* stream);
+
+/*
+ * The same step for HOST-resident inputs and outputs (what a data-loader thread hands over and what the T5 side of
+ * prepare_input consumes): copies the pinned host query halves and the host-tokenised prefix CSR to the device
+ * staging buffers named in `a` / `io`, runs mpr_retrieve, and copies ONE contiguous result block back:
+ *   d_out/h_out layout = whatever the caller laid out behind a->input_ids ... (the block [d_out, d_out + out_bytes)
+ *   must contain every output pointer of `a` that the caller wants on the host).
+ * Everything is asynchronous on `stream`; with sync != 0 the call returns after the results are in h_out.
+ * h_q0 == NULL: the queries are already on the device (a->q0 / a->q_bf16 as in mpr_retrieve).
+ */
+typedef struct mpr_host_io {
+    const void* h_q0;          /* pinned host [b][d0] of a->q_dtype, copied to a->q0 */
+    const void* h_q1;          /* pinned host [b][d1] or NULL, copied to a->q1       */
+    const int32_t* h_prefix_ids;
+    int n_prefix_ids;          /* copied to a->prefix_ids                            */
+    const int32_t* h_prefix_off; /* [b+1], copied to a->prefix_off                   */
+    const void* d_out;         /* device result block                                */
+    void* h_out;               /* pinned host result block                           */
+    size_t out_bytes;
+    int sync;
+} mpr_host_io;
+
+int mpr_retrieve_host(mpr_handle_t h, const mpr_retrieve_args* a, const mpr_host_io* io, void* stream);
+
+/* Seconds a rank waits for a peer's candidates inside a sharded search before giving up (default 60). */
+int mpr_set_exchange_timeout(mpr_handle_t h, double seconds);
+
+/*
+ * Kernel 5 — prompt token ids -> T5 input embeddings with the image tokens prepended, forward only.
+ * Replaces: T5_model.shared(input_ids), torch.ones image mask, and the two torch.cat calls of
+ *           architectures/T5VisionModel.py:169-176.
+ * input_ids / attention_mask: int64 [b][in_stride] on the device (kernel 3's outputs), first `len` columns used.
+ * table [vocab][hidden] and image_tokens [b][n_image][hidden] (may be NULL with n_image = 0: "only use question",
+ * :178-180) share table_dtype (MPR_SRC_*).  out_embeds [b][n_image+len][hidden] in the same dtype;
+ * out_mask [b][n_image+len] is float32 (mask_f32 != 0: what the reference's cat of a float ones tensor with the int64
+ * tokenizer mask promotes to) or int64.  An id outside [0, vocab) zero-fills its row and sets the device error word.
+ */
+int mpr_embed_prompt(mpr_handle_t h, const int64_t* input_ids, const int64_t* attention_mask, int b, int len,
+                     int in_stride, const void* table, int table_dtype, int vocab, int hidden,
+                     const void* image_tokens, int n_image, void* out_embeds, void* out_mask, int mask_f32,
+                     void* stream);
+
+/*
+ * Tuning aid: with MPR_DEBUG_COUNTERS=1 in the environment at mpr_create the scan kernel counts, since the last call,
+ * [0] candidates admitted past the thresholds, [1] warp-level list flushes, [2] 8-score groups that took the admission
+ * path, [3] list replacements, [4] warp-tiles processed, [5] threshold refreshes that found a shared bound.  Synchronises
+ * the device; returns zeros when the counters are off.
+ */
+int mpr_debug_counters(mpr_handle_t h, uint64_t* out8);
+/* With the same switch: out[16*cta + k] = globaltimer (ns) at event k of CTA cta in the LAST scan launch (k: 0 entry,
+ * 1 q-tile ready, 2 producer done, 3/5 epilogue group 0/1 left its tile loop, 4/6 its partial lists written, 7 CTA done,
+ * 8 past the grid barrier, 9 tail done, 10 second tile's data arrived, 11/12 first and 13/14 fourth tile consumed). */
+int mpr_debug_timeline(mpr_handle_t h, uint64_t* out, int n_ctas);
+
+/* Kernel launches issued by the last mpr_retrieve / mpr_retrieve_host on this handle (bench bookkeeping). */
+int mpr_last_launch_count(mpr_handle_t h);
+
+/*
  * Debug / test aid: the full [b][n_local] score matrix through the SAME tcgen05 pipeline as mpr_search_topk
  * (the kernel is instantiated with a dump epilogue).  Small shapes only.
  */
@@ -139,8 +254,8 @@ int mpr_debug_scores(mpr_handle_t h, const uint16_t* q, int b, const uint16_t* b
                      int64_t n_local, int d, float* scores, void* workspace, size_t workspace_bytes, void* stream);
 
 /*
- * Measurement aid for bench.py's roofline: between begin and end every scan-kernel launch (kernel 2 only, not the
- * merge) is bracketed by a cudaEvent pair on the launching stream.  mpr_profile_end synchronises on the last event and
+ * Measurement aid for bench.py's roofline: between begin and end every scan-kernel launch (kernel 2 including its
+ * fused tail, not a separate tail launch) is bracketed by a cudaEvent pair on the launching stream.  mpr_profile_end synchronises on the last event and
  * returns the summed device time and the number of launches.  At most max_launches launches are recorded.
  */
 int mpr_profile_begin(mpr_handle_t h, int max_launches);

@@ -15,12 +15,45 @@ LIB_PATH = os.path.join(_HERE, "lib", "libmpr_b200.so")
 MPR_MAX_KK = 32
 SRC_F32, SRC_F16, SRC_BF16 = 0, 1, 2
 
+ABI_VERSION = 2
+STATUS_XCHG_TIMEOUT = 201
+
 EXPORTS = [
     "mpr_abi_version", "mpr_create", "mpr_destroy", "mpr_last_error", "mpr_device_error", "mpr_bank_build",
     "mpr_search_workspace_bytes", "mpr_search_topk", "mpr_merge_topk", "mpr_prompt_gather", "mpr_debug_scores",
-    "mpr_search_plan", "mpr_profile_begin", "mpr_profile_end", "mpr_profile_launch_ms", "mpr_exchange_bytes", "mpr_exchange_push", "mpr_exchange_merge",
-    "mpr_search_fused_supported", "mpr_search_topk_fused",
+    "mpr_search_plan", "mpr_profile_begin", "mpr_profile_end", "mpr_profile_launch_ms", "mpr_exchange_bytes",
+    "mpr_search_fused_supported", "mpr_search_topk_fused", "mpr_retrieve", "mpr_retrieve_host",
+    "mpr_set_exchange_timeout", "mpr_embed_prompt", "mpr_last_launch_count", "mpr_debug_counters", "mpr_debug_timeline",
 ]
+
+
+class RetrieveArgs(C.Structure):
+    """``mpr_retrieve_args`` of include/mpr_b200.h, field for field."""
+    _fields_ = [
+        ("q0", C.c_void_p), ("q1", C.c_void_p), ("d0", C.c_int), ("d1", C.c_int), ("q_dtype", C.c_int),
+        ("normalise", C.c_int), ("q_bf16", C.c_void_p), ("q_scratch", C.c_void_p), ("b", C.c_int),
+        ("bank", C.c_void_p), ("bias", C.c_void_p), ("n_local", C.c_int64), ("idx_base", C.c_int64),
+        ("d", C.c_int), ("kk", C.c_int),
+        ("out_keys", C.c_void_p), ("out_score", C.c_void_p), ("out_idx", C.c_void_p), ("out_q_bias", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+        ("rank", C.c_int), ("world", C.c_int), ("xchg_cap", C.c_int), ("peer_bufs", C.POINTER(C.c_void_p)),
+        ("skip", C.c_int), ("answer_id", C.c_void_p), ("bucket_lut", C.c_void_p), ("prefix_ids", C.c_void_p),
+        ("prefix_off", C.c_void_p), ("seg_ids", C.c_void_p), ("seg_off", C.c_void_p),
+        ("use_quantifier", C.c_int), ("pad_id", C.c_int), ("eos_id", C.c_int), ("max_len", C.c_int),
+        ("out_stride", C.c_int),
+        ("input_ids", C.c_void_p), ("attention_mask", C.c_void_p), ("out_len", C.c_void_p), ("maj_answer", C.c_void_p),
+        ("maj_count", C.c_void_p), ("bucket", C.c_void_p), ("ret_answer", C.c_void_p), ("status", C.c_void_p),
+    ]
+
+
+class HostIO(C.Structure):
+    """``mpr_host_io`` of include/mpr_b200.h."""
+    _fields_ = [
+        ("h_q0", C.c_void_p), ("h_q1", C.c_void_p), ("h_prefix_ids", C.c_void_p), ("n_prefix_ids", C.c_int),
+        ("h_prefix_off", C.c_void_p), ("d_out", C.c_void_p), ("h_out", C.c_void_p), ("out_bytes", C.c_size_t),
+        ("sync", C.c_int),
+    ]
+
 
 _lib: Optional[C.CDLL] = None
 
@@ -75,12 +108,25 @@ def load() -> C.CDLL:
     lib.mpr_search_topk_fused.argtypes = [vp, vp, i32, vp, i32, i32, i32, i32, vp, vp, i64, i64, i32, vp, vp, vp, vp, vp, sz, vp]
     lib.mpr_exchange_bytes.restype = sz
     lib.mpr_exchange_bytes.argtypes = [i32, i32]
-    lib.mpr_exchange_push.restype = i32
-    lib.mpr_exchange_push.argtypes = [vp, vp, i32, i32, i32, i32, C.POINTER(vp), i32, vp]
-    lib.mpr_exchange_merge.restype = i32
-    lib.mpr_exchange_merge.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]
+    lib.mpr_retrieve.restype = i32
+    lib.mpr_retrieve.argtypes = [vp, C.POINTER(RetrieveArgs), vp]
+    lib.mpr_retrieve_host.restype = i32
+    lib.mpr_retrieve_host.argtypes = [vp, C.POINTER(RetrieveArgs), C.POINTER(HostIO), vp]
+    lib.mpr_set_exchange_timeout.restype = i32
+    lib.mpr_set_exchange_timeout.argtypes = [vp, C.c_double]
+    lib.mpr_embed_prompt.restype = i32
+    lib.mpr_embed_prompt.argtypes = [vp, vp, vp, i32, i32, i32, vp, i32, i32, i32, vp, i32, vp, vp, i32, vp]
+    lib.mpr_debug_timeline.restype = i32
+    lib.mpr_debug_timeline.argtypes = [vp, C.POINTER(C.c_uint64), i32]
+    lib.mpr_debug_counters.restype = i32
+    lib.mpr_debug_counters.argtypes = [vp, C.POINTER(C.c_uint64)]
+    lib.mpr_last_launch_count.restype = i32
+    lib.mpr_last_launch_count.argtypes = [vp]
     lib.mpr_profile_launch_ms.restype = i32
     lib.mpr_profile_launch_ms.argtypes = [vp, i32, C.POINTER(C.c_float)]
+    if lib.mpr_abi_version() != ABI_VERSION:
+        raise NativeError(f"{LIB_PATH} has ABI version {lib.mpr_abi_version()}, this package needs {ABI_VERSION}: rebuild it "
+                          "with `python -m multimodalpromptretrieval_b200.csrc.build --force`")
     _lib = lib
     return lib
 

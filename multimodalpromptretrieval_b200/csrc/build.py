@@ -13,7 +13,7 @@ PKG = os.path.dirname(HERE)
 ROOT = os.path.dirname(PKG)
 OUT = os.path.join(PKG, "lib", "libmpr_b200.so")
 SOURCES = ["mpr_abi.cu"]
-HEADERS = ["ptx.cuh", "topk_key.cuh", "scan_topk.cuh", "bank_build.cuh", "merge_topk.cuh", "prompt_gather.cuh", "exchange.cuh",
+HEADERS = ["ptx.cuh", "topk_key.cuh", "scan_topk.cuh", "bank_build.cuh", "merge_topk.cuh", "prompt_gather.cuh", "tail.cuh", "embed_gather.cuh",
            os.path.join(ROOT, "include", "mpr_b200.h")]
 
 NVCC_FLAGS = [

@@ -1,5 +1,6 @@
 // C-ABI entry points (include/mpr_b200.h): argument validation, launch planning, TMA descriptor encoding and
-// kernel launches.  No device synchronisation, no persistent device allocations beyond one error word.
+// kernel launches.  No device synchronisation (except where the caller asks for it in mpr_retrieve_host), no persistent
+// device allocations beyond one error word.
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -12,10 +13,11 @@
 
 #include "../../include/mpr_b200.h"
 #include "bank_build.cuh"
-#include "exchange.cuh"
+#include "embed_gather.cuh"
 #include "merge_topk.cuh"
 #include "prompt_gather.cuh"
 #include "scan_topk.cuh"
+#include "tail.cuh"
 
 using namespace mpr;
 
@@ -27,17 +29,30 @@ struct mpr_context {
     int device = -1;
     int num_sms = 0;
     int* d_err = nullptr;
+    unsigned long long* d_dbg = nullptr;    // debug counters + timeline, allocated only with MPR_DEBUG_COUNTERS=1|2
+    int dbg_counters = 0;                   // 1: the event counters are live (their atomics distort timings); 2: timeline only
     PFN_encodeTiled encode = nullptr;
     std::vector<cudaEvent_t> prof_events;   // start/stop pairs, used only between mpr_profile_begin/end
     int cand_cap_override = 0;              // MPR_CAND_CAP=10..16 forces the pending-buffer depth
-    int epi_groups = 2;                     // MPR_EPI_GROUPS=1 forces a single epilogue group
+    int epi_groups = 0;                     // MPR_EPI_GROUPS=1|2 forces the epilogue group count (0 = planner's choice)
     int stage_subs = 4;                     // max 64-wide K sub-chunks per ring stage (MPR_STAGE_SUBS=1|2|4)
     int use_q_tmem = 1;                     // q-tile as TMEM A operand when D <= 512 (MPR_NO_QTMEM=1 disables)
     int use_cluster = 1;                    // CTA-pair TMA multicast in the tensor-bound regime (MPR_NO_CLUSTER=1 disables)
+    int dynamic_tiles = 1;                  // tiles pulled from an atomic counter (MPR_STATIC_TILES=1: contiguous ranges)
+    int shared_thr = 1;                     // shared admission thresholds (MPR_NO_GTHR=1 disables)
+    int fused_tail = 1;                     // single-wave grids finish the step in the scan launch (MPR_NO_FUSED_TAIL=1)
+    int cooperative = 1;                    // fused-tail launches are cooperative (MPR_NO_COOP=1: plain launch)
+    int use_reg_list = 1;                   // k + skip <= 8: lists in registers (MPR_NO_REGLIST=1: shared memory)
+    unsigned long long xchg_timeout_ns = 60ull * 1000000000ull;
+    const void* ws_ptr = nullptr;           // workspace whose control words are known to be zero ...
+    size_t ws_zeroed = 0;                   // ... over this many leading bytes
+    int last_launches = 0;                  // kernel launches of the last mpr_retrieve
     int prof_used = -1;                     // -1 = profiling off
     int prof_last_n = 0;                    // launches recorded by the last begin/end pair
     char err[512] = {0};
 };
+
+constexpr int kDbgWords = 8 + 16 * 2048;   // event counters + a 16-slot timeline for up to 2048 CTAs
 
 static thread_local char g_err[512] = "";
 
@@ -59,23 +74,39 @@ static int fail(mpr_context* h, int code, const char* fmt, ...) {
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 static inline int pow2_ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+static inline size_t round16(size_t v) { return (v + 15u) & ~size_t(15); }
+
+// Every ABI call runs on the handle's device whatever the caller's current device is, and leaves the caller's current
+// device untouched.
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != device) switched = cudaSetDevice(device) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (switched) cudaSetDevice(prev);
+    }
+};
 
 // ------------------------------------------------------------------------------------------------ planning
 struct ScanPlan {
     int n_chunks, q_tile, q_box_rows, n_qtiles, n_splits, n_tiles, n_stages, kk_pad, cand_cap, sub_per_stage, n_epi_groups;
     bool q_tmem;       // q-tile in tensor memory (TMEM A operand) instead of shared memory
+    bool reg_list;     // k + skip <= 8: per-query lists in registers (no list / pending memory in shared memory)
     uint32_t smem_bytes;
 };
 
 static int make_plan(mpr_context* h, int b, int64_t n_local, int d, int kk, ScanPlan* pl) {
     if (b < 1) return fail(h, MPR_EINVAL, "b must be >= 1 (got %d)", b);
-    if (n_local < 1 || n_local >= (1ll << 31) - kTileRows)
+    if (n_local < 0 || n_local >= (1ll << 31) - kTileRows)      // 0 = a rank whose shard is empty still takes part in the exchange
         return fail(h, MPR_EINVAL, "n_local out of range (got %lld)", static_cast<long long>(n_local));
     if (d < 64 || d > 4096 || d % 64 != 0) return fail(h, MPR_EINVAL, "d must be a multiple of 64 in [64, 4096] (got %d)", d);
     if (kk < 1 || kk > MPR_MAX_KK) return fail(h, MPR_EINVAL, "k + skip must be in [1, %d] (got %d)", MPR_MAX_KK, kk);
 
     pl->n_chunks = d / kChunkK;
-    pl->kk_pad = pow2_ceil(kk);
+    pl->reg_list = h->use_reg_list && kk <= 8;
+    pl->kk_pad = pl->reg_list ? 0 : pow2_ceil(kk);
     pl->n_tiles = static_cast<int>((n_local + kTileRows - 1) / kTileRows);
     // D <= 512: the q-tile (128 x D bf16) fits 256 TMEM columns next to two 128-column accumulators
     pl->q_tmem = h->use_q_tmem && d <= 512;
@@ -96,19 +127,21 @@ static int make_plan(mpr_context* h, int b, int64_t n_local, int d, int kk, Scan
             pl->q_box_rows = q_tile_max;
         }
         if (pl->q_tmem) pl->q_box_rows = 0;       // nothing of Q in shared memory
-        // List maintenance dominates for k+s >= 16: one epilogue group (one list per query instead of two, ~1.8x less
-        // insert work); otherwise two groups.
-        // The second group's lists must also not starve the bank ring (SS mode keeps 64-128 KiB of Q in shared memory).
+        // Two epilogue groups (two lists per query) unless the second group's lists would starve the bank ring
+        // (SS mode keeps 64-128 KiB of Q in shared memory, and a k+s = 32 list is 392 B per query).  With the shared
+        // admission thresholds list maintenance is off the critical path for every k, so k no longer decides this.
         // (deeper pending buffers were measured to HURT: 32 slots -> +25 % at k+s = 16/32, because the admission
         // threshold only moves at a flush and a stale threshold admits many more candidates)
         const int caps1[] = {16, 14, 12, 10, 10}, caps2[] = {16, 14, 12, 10};
+        const int caps0[] = {0};                       // register lists: no pending buffer either
         auto units_for = [&](int cap, int groups) {   // 16 KiB ring units left beside the resident q-tile and the lists
             const ScanSmemLayout fixed = scan_smem_layout(pl->n_chunks, pl->q_box_rows, pl->kk_pad, cap, 0, 1, groups);
             return (kMaxSmem - 1024 - static_cast<int>(fixed.total)) / kStageBytes;
         };
-        pl->n_epi_groups = (h->epi_groups == 1 || pl->kk_pad >= 16 || units_for(16, 2) < 6) ? 1 : 2;
-        const int* caps = pl->n_epi_groups == 1 ? caps1 : caps2;
-        const int n_caps = pl->n_epi_groups == 1 ? 5 : 4;
+        pl->n_epi_groups = (!pl->reg_list && units_for(16, 2) < 6) ? 1 : 2;
+        if (h->epi_groups == 1 || (h->epi_groups == 2 && units_for(10, 2) >= 3)) pl->n_epi_groups = h->epi_groups;
+        const int* caps = pl->reg_list ? caps0 : pl->n_epi_groups == 1 ? caps1 : caps2;
+        const int n_caps = pl->reg_list ? 1 : pl->n_epi_groups == 1 ? 5 : 4;
         pl->cand_cap = caps[n_caps - 1];
         stages = units_for(pl->cand_cap, pl->n_epi_groups);
         for (int want : {6, 3}) {
@@ -121,7 +154,7 @@ static int make_plan(mpr_context* h, int b, int64_t n_local, int d, int kk, Scan
                 }
             if (found) break;
         }
-        if (h->cand_cap_override >= 10 && h->cand_cap_override <= kCandCapMax && units_for(h->cand_cap_override, pl->n_epi_groups) >= 3) {
+        if (!pl->reg_list && h->cand_cap_override >= 10 && h->cand_cap_override <= kCandCapMax && units_for(h->cand_cap_override, pl->n_epi_groups) >= 3) {
             pl->cand_cap = h->cand_cap_override;      // tuning knob (MPR_CAND_CAP)
             stages = units_for(pl->cand_cap, pl->n_epi_groups);
         }
@@ -146,6 +179,23 @@ static int make_plan(mpr_context* h, int b, int64_t n_local, int d, int kk, Scan
     return MPR_OK;
 }
 
+// Workspace = [control block | tile counters | shared thresholds] (all-zero between launches) + partial lists.
+struct WsLayout {
+    size_t tile_ctr_off, gthr_off, zero_bytes, part_off, total;
+    int ns;
+};
+
+static WsLayout ws_layout(const ScanPlan& pl, int b, int kk) {
+    WsLayout w;
+    w.ns = (kk + 3) & ~3;
+    w.tile_ctr_off = 16;
+    w.gthr_off = round16(w.tile_ctr_off + sizeof(uint32_t) * static_cast<size_t>(pl.n_qtiles));
+    w.zero_bytes = w.gthr_off + sizeof(uint32_t) * static_cast<size_t>(b) * w.ns;
+    w.part_off = round16(w.zero_bytes);
+    w.total = w.part_off + static_cast<size_t>(pl.n_splits) * kEpiGroups * b * kk * sizeof(uint64_t);
+    return w;
+}
+
 static int encode_2d(mpr_context* h, CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols,
                      uint32_t box_rows) {
     cuuint64_t dims[2] = {cols, rows};
@@ -161,30 +211,91 @@ static int encode_2d(mpr_context* h, CUtensorMap* map, const void* ptr, uint64_t
     return MPR_OK;
 }
 
-struct FusedQ {            // raw query halves for the fused-cast variant (src0 == nullptr: q is already bf16)
-    const void* src0 = nullptr;
-    const void* src1 = nullptr;
-    int d0 = 0, d1 = 0, dtype = 0, normalise = 0;
-    float* q_bias_out = nullptr;
-};
+template <typename Kern>
+static cudaError_t launch_kernel(Kern kern, dim3 grid, uint32_t smem, cudaStream_t st, int cluster, bool cooperative,
+                                 const CUtensorMap& tq, const CUtensorMap& tb, const ScanParams& p, const TailParams& t) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kScanThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    int n = 0;
+    if (cluster > 1) {
+        attr[n].id = cudaLaunchAttributeClusterDimension;
+        attr[n].val.clusterDim.x = cluster;
+        attr[n].val.clusterDim.y = 1;
+        attr[n].val.clusterDim.z = 1;
+        ++n;
+    }
+    if (cooperative) {
+        attr[n].id = cudaLaunchAttributeCooperative;
+        attr[n].val.cooperative = 1;
+        ++n;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = n;
+    return cudaLaunchKernelEx(&cfg, kern, tq, tb, p, t);
+}
 
+// One retrieval step on the device: [kernel 1] -> scan (+ fused tail) -> [stand-alone tail].
 template <bool kDump>
-static int launch_scan(mpr_context* h, const ScanPlan& pl, const uint16_t* q, int b, const uint16_t* bank,
-                       const float* bias, int64_t n_local, int64_t idx_base, int d, int kk, uint64_t* part_keys,
-                       float* dump, cudaStream_t st, const FusedQ& fq = FusedQ()) {
-    CUtensorMap tq, tb;
-    int rc = MPR_OK;
-    if (pl.q_tmem) memset(&tq, 0, sizeof(tq));       // the TMEM variant never touches the Q tensor map
-    else rc = encode_2d(h, &tq, q, static_cast<uint64_t>(b), static_cast<uint64_t>(d), pl.q_box_rows);
+static int run_step(mpr_context* h, const mpr_retrieve_args& a, float* dump, cudaStream_t st) {
+    const int b = a.b, kk = a.kk, d = a.d;
+    ScanPlan pl;
+    const int saved_reg = h->use_reg_list;
+    if (kDump) h->use_reg_list = 0;            // the dump epilogue exists for the shared-memory-list variant only
+    int rc = make_plan(h, b, a.n_local, d, kk, &pl);
+    h->use_reg_list = saved_reg;
     if (rc) return rc;
+    const WsLayout wl = ws_layout(pl, b, kk);
+    if (a.workspace_bytes < wl.total)
+        return fail(h, MPR_EWORKSPACE, "workspace too small: %zu < %zu", a.workspace_bytes, wl.total);
+    h->last_launches = 0;
+
+    // ---- which kernel variant
+    bool raw = a.q0 != nullptr;
+    const uint16_t* q_bf16 = a.q_bf16;
     // tensor-bound regime with an even number of q-tiles: CTA pairs share each bank chunk by TMA multicast
-    const bool pair = !kDump && !pl.q_tmem && h->use_cluster && pl.n_qtiles >= 2 && pl.n_qtiles % 2 == 0;
-    rc = encode_2d(h, &tb, bank, static_cast<uint64_t>(n_local), static_cast<uint64_t>(d), pair ? kTileRows / 2 : kTileRows);
+    bool pair = !kDump && !pl.q_tmem && h->use_cluster && pl.n_qtiles >= 2 && pl.n_qtiles % 2 == 0;
+    if (raw && pair) {
+        if (a.q_scratch) {     // the pair variant takes prepared queries: one kernel-1 launch into the caller's scratch
+            const int threads = 256, rows_per_block = threads / 32;
+            bank_build_kernel<<<(b + rows_per_block - 1) / rows_per_block, threads, 0, st>>>(
+                a.q0, a.d0, a.q1, a.q1 ? a.d1 : 0, a.q_dtype, b, a.normalise, a.q_scratch, a.out_q_bias);
+            CUDA_TRY(h, cudaGetLastError());
+            ++h->last_launches;
+            q_bf16 = a.q_scratch;
+            raw = false;
+        } else {
+            pair = false;
+        }
+    }
+    if (raw && !pl.q_tmem && d > 2048)
+        return fail(h, MPR_EINVAL, "raw queries are supported up to D = 2048 (got %d); prepare them with mpr_bank_build", d);
+    if (!raw && !q_bf16) return fail(h, MPR_EINVAL, "no queries: q0 and q_bf16 are both null");
+
+    CUtensorMap tq, tb;
+    if (pl.q_tmem || raw) memset(&tq, 0, sizeof(tq));       // the warps bring the q-tile in; no Q tensor map
+    else rc = encode_2d(h, &tq, q_bf16, static_cast<uint64_t>(b), static_cast<uint64_t>(d), pl.q_box_rows);
     if (rc) return rc;
+    if (a.n_local > 0) rc = encode_2d(h, &tb, a.bank, static_cast<uint64_t>(a.n_local), static_cast<uint64_t>(d), pair ? kTileRows / 2 : kTileRows);
+    else memset(&tb, 0, sizeof(tb));                         // no tiles: the bank map is never dereferenced
+    if (rc) return rc;
+
+    const dim3 grid(pl.n_splits * pl.n_qtiles);
+    const bool fused_tail = !kDump && !pair && h->fused_tail && static_cast<int>(grid.x) <= h->num_sms;
+    unsigned char* ws = static_cast<unsigned char*>(a.workspace);
+    if (!kDump) {
+        // control words must be zero before the first launch on this workspace; every launch leaves them zero again
+        if (ws != h->ws_ptr || wl.zero_bytes > h->ws_zeroed) CUDA_TRY(h, cudaMemsetAsync(ws, 0, wl.zero_bytes, st));
+        h->ws_ptr = ws;
+        h->ws_zeroed = wl.zero_bytes;
+    }
 
     ScanParams p;
     p.b_total = b;
-    p.n_local = static_cast<int>(n_local);
+    p.n_local = static_cast<int>(a.n_local);
     p.n_chunks = pl.n_chunks;
     p.kk = kk;
     p.kk_pad = pl.kk_pad;
@@ -197,50 +308,128 @@ static int launch_scan(mpr_context* h, const ScanPlan& pl, const uint16_t* q, in
     p.n_stages = pl.n_stages;
     p.sub_per_stage = pl.sub_per_stage;
     p.n_epi_groups = pl.n_epi_groups;
-    p.idx_base = static_cast<uint32_t>(idx_base);
+    p.idx_base = static_cast<uint32_t>(a.idx_base);
     p.bank_policy = pl.n_qtiles == 1 ? ptx::kEvictFirst : ptx::kEvictNormal;
-    p.bias = bias;
-    p.q = q;
+    p.bias = a.bias;
+    p.q = q_bf16;
     p.d = d;
-    p.qsrc0 = fq.src0;
-    p.qsrc1 = fq.src1;
-    p.qd0 = fq.d0;
-    p.qd1 = fq.d1;
-    p.q_dtype = fq.dtype;
-    p.q_normalise = fq.normalise;
-    p.q_bias_out = fq.q_bias_out;
-    p.part_keys = part_keys;
+    p.qsrc0 = raw ? a.q0 : nullptr;
+    p.qsrc1 = raw ? a.q1 : nullptr;
+    p.qd0 = a.d0;
+    p.qd1 = a.q1 ? a.d1 : 0;
+    p.q_dtype = a.q_dtype;
+    p.q_normalise = a.normalise;
+    p.q_bias_out = raw ? a.out_q_bias : nullptr;
+    p.part_keys = reinterpret_cast<uint64_t*>(ws + wl.part_off);
+    p.tile_ctr = (!kDump && !pair && h->dynamic_tiles) ? reinterpret_cast<uint32_t*>(ws + wl.tile_ctr_off) : nullptr;
+    p.gthr = (!kDump && h->shared_thr) ? reinterpret_cast<uint32_t*>(ws + wl.gthr_off) : nullptr;
+    p.ns = wl.ns;
+    p.fused_tail = fused_tail ? 1 : 0;
+    p.dbg = h->dbg_counters ? h->d_dbg : nullptr;
+    p.dbg_ts = h->d_dbg ? h->d_dbg + 8 : nullptr;
     p.dump = dump;
     p.err = h->d_err;
 
-    const dim3 grid(pl.n_splits * pl.n_qtiles);
+    TailParams t;
+    memset(&t, 0, sizeof(t));
+    t.b = b;
+    t.kk = kk;
+    t.part_keys = p.part_keys;
+    t.n_lists = pl.n_splits * kEpiGroups;
+    t.ctrl = reinterpret_cast<uint32_t*>(ws);
+    t.tile_ctr = reinterpret_cast<uint32_t*>(ws + wl.tile_ctr_off);
+    t.n_tile_ctr = pl.n_qtiles;
+    t.gthr = p.gthr;
+    t.ns = wl.ns;
+    t.out_keys = a.out_keys;
+    t.out_score = a.out_score;
+    t.out_idx = a.out_idx;
+    t.status = a.status;
+    t.xchg.world = a.world > 1 ? a.world : 1;
+    t.xchg.rank = a.world > 1 ? a.rank : 0;
+    t.xchg.cap = a.xchg_cap;
+    t.xchg.timeout_ns = h->xchg_timeout_ns;
+    if (a.world > 1)
+        for (int r = 0; r < a.world; ++r) t.xchg.peers.buf[r] = static_cast<unsigned char*>(a.peer_bufs[r]);
+    if (a.answer_id) {
+        PromptParams& pp = t.prompt;
+        pp.idx = nullptr; pp.b = b; pp.kk = kk; pp.skip = a.skip;
+        pp.answer_id = a.answer_id; pp.bucket_lut = a.bucket_lut;
+        pp.prefix_ids = a.prefix_ids; pp.prefix_off = a.prefix_off; pp.seg_ids = a.seg_ids; pp.seg_off = a.seg_off;
+        pp.use_quantifier = a.use_quantifier; pp.pad_id = a.pad_id; pp.eos_id = a.eos_id;
+        pp.max_len = a.max_len; pp.out_stride = a.out_stride;
+        pp.input_ids = reinterpret_cast<long long*>(a.input_ids);
+        pp.attention_mask = reinterpret_cast<long long*>(a.attention_mask);
+        pp.out_len = a.out_len; pp.maj_answer = a.maj_answer; pp.maj_count = a.maj_count; pp.bucket = a.bucket;
+        pp.ret_answer = a.ret_answer;
+    }
+
     const bool prof = h->prof_used >= 0 && 2 * (h->prof_used + 1) <= static_cast<int>(h->prof_events.size());
     if (prof) CUDA_TRY(h, cudaEventRecord(h->prof_events[2 * h->prof_used], st));
-    if (pair) {
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = grid;
-        cfg.blockDim = dim3(kScanThreads);
-        cfg.dynamicSmemBytes = pl.smem_bytes;
-        cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        CUDA_TRY(h, cudaLaunchKernelEx(&cfg, scan_topk_kernel<false, 2, false>, tq, tb, p));
-    } else if (pl.q_tmem && fq.src0) {
-        scan_topk_kernel<false, 1, true, true><<<grid, kScanThreads, pl.smem_bytes, st>>>(tq, tb, p);
-    } else if (pl.q_tmem) {
-        scan_topk_kernel<kDump, 1, true><<<grid, kScanThreads, pl.smem_bytes, st>>>(tq, tb, p);
+    const bool coop = fused_tail && h->cooperative;
+    cudaError_t le;
+    const uint32_t sm = pl.smem_bytes;
+#define MPR_LAUNCH(DUMP, CL, QT, FQ, RL, COOP) \
+    launch_kernel(scan_topk_kernel<DUMP, CL, QT, FQ, RL>, grid, sm, st, CL, COOP, tq, tb, p, t)
+    if (pl.reg_list && !kDump) {
+        if (pair)                     le = MPR_LAUNCH(false, 2, false, false, true, false);
+        else if (pl.q_tmem && raw)    le = MPR_LAUNCH(false, 1, true, true, true, coop);
+        else if (pl.q_tmem)           le = MPR_LAUNCH(false, 1, true, false, true, coop);
+        else if (raw)                 le = MPR_LAUNCH(false, 1, false, true, true, coop);
+        else                          le = MPR_LAUNCH(false, 1, false, false, true, coop);
     } else {
-        scan_topk_kernel<kDump, 1, false><<<grid, kScanThreads, pl.smem_bytes, st>>>(tq, tb, p);
+        if (pair)                     le = MPR_LAUNCH(false, 2, false, false, false, false);
+        else if (pl.q_tmem && raw)    le = MPR_LAUNCH(false, 1, true, true, false, coop);
+        else if (pl.q_tmem)           le = MPR_LAUNCH(kDump, 1, true, false, false, coop);
+        else if (raw)                 le = MPR_LAUNCH(false, 1, false, true, false, coop);
+        else                          le = MPR_LAUNCH(kDump, 1, false, false, false, coop);
     }
-    CUDA_TRY(h, cudaGetLastError());
+#undef MPR_LAUNCH
+    if (le != cudaSuccess) return fail(h, MPR_ECUDA, "scan launch failed: %s", cudaGetErrorString(le));
+    ++h->last_launches;
     if (prof) {
         CUDA_TRY(h, cudaEventRecord(h->prof_events[2 * h->prof_used + 1], st));
         ++h->prof_used;
+    }
+    if (!kDump && !fused_tail) {
+        const int warps_per_block = 4;
+        tail_kernel<<<(b + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(t);
+        CUDA_TRY(h, cudaGetLastError());
+        ++h->last_launches;
+    }
+    return MPR_OK;
+}
+
+static int validate_retrieve(mpr_context* h, const mpr_retrieve_args* a) {
+    if (!a) return fail(h, MPR_EINVAL, "null argument block");
+    if (a->b == 0) return MPR_OK;
+    if (!a->workspace || (a->n_local > 0 && (!a->bank || !a->bias)))
+        return fail(h, MPR_EINVAL, "null pointer (bank, bias or workspace)");
+    if (!aligned16(a->bank) || !aligned16(a->workspace) || !aligned16(a->q0) || !aligned16(a->q1) || !aligned16(a->q_bf16) ||
+        !aligned16(a->q_scratch))
+        return fail(h, MPR_EINVAL, "queries, bank and workspace must be 16-byte aligned");
+    if (a->idx_base < 0 || a->idx_base + a->n_local >= 0xFFFFFFFFll) return fail(h, MPR_EINVAL, "global row index exceeds 32 bits");
+    if (a->q0) {
+        const int d1 = a->q1 ? a->d1 : 0;
+        if (a->d0 < 8 || a->d0 % 8 || d1 % 8 || a->d0 + d1 != a->d)
+            return fail(h, MPR_EINVAL, "query halves must be multiples of 8 wide and add up to d (d0=%d d1=%d d=%d)", a->d0, d1, a->d);
+        if (a->q_dtype < MPR_SRC_F32 || a->q_dtype > MPR_SRC_BF16) return fail(h, MPR_EINVAL, "bad q_dtype %d", a->q_dtype);
+    }
+    if (a->world > 1) {
+        if (a->world > kXchgMaxWorld || a->rank < 0 || a->rank >= a->world)
+            return fail(h, MPR_EINVAL, "bad rank/world %d/%d (max world %d)", a->rank, a->world, kXchgMaxWorld);
+        if (!a->peer_bufs) return fail(h, MPR_EINVAL, "peer_bufs is null");
+        for (int r = 0; r < a->world; ++r)
+            if (!a->peer_bufs[r] || !aligned16(a->peer_bufs[r])) return fail(h, MPR_EINVAL, "peer buffer %d is null or unaligned", r);
+        if (static_cast<long long>(a->b) * a->kk > a->xchg_cap)
+            return fail(h, MPR_EINVAL, "b*kk = %lld exceeds the exchange capacity %d", static_cast<long long>(a->b) * a->kk, a->xchg_cap);
+    }
+    if (a->answer_id) {
+        if (!a->bucket_lut || !a->prefix_ids || !a->prefix_off || !a->seg_ids || !a->seg_off || !a->input_ids ||
+            !a->attention_mask || !a->out_len || !a->maj_answer || !a->maj_count || !a->bucket)
+            return fail(h, MPR_EINVAL, "prompt stage: null pointer");
+        if (a->skip < 0 || a->skip >= a->kk) return fail(h, MPR_EINVAL, "need 0 <= skip < kk (kk=%d skip=%d)", a->kk, a->skip);
+        if (a->max_len < 1 || a->out_stride < 1) return fail(h, MPR_EINVAL, "max_len and out_stride must be >= 1");
     }
     return MPR_OK;
 }
@@ -255,7 +444,10 @@ const char* mpr_last_error(mpr_handle_t h) { return h ? h->err : g_err; }
 int mpr_create(int device, mpr_handle_t* out) {
     if (!out) return fail(nullptr, MPR_EINVAL, "out is null");
     *out = nullptr;
-    CUDA_TRY(nullptr, cudaSetDevice(device));
+    DeviceGuard guard(device);       // the caller's current device is restored on return
+    int cur = -1;
+    CUDA_TRY(nullptr, cudaGetDevice(&cur));
+    if (cur != device) CUDA_TRY(nullptr, cudaSetDevice(device));
     cudaDeviceProp prop;
     CUDA_TRY(nullptr, cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10)
@@ -274,29 +466,44 @@ int mpr_create(int device, mpr_handle_t* out) {
     h->encode = reinterpret_cast<PFN_encodeTiled>(fn);
     e = cudaMalloc(&h->d_err, sizeof(int));
     if (e == cudaSuccess) e = cudaMemset(h->d_err, 0, sizeof(int));
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(scan_topk_kernel<false, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(scan_topk_kernel<true, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(scan_topk_kernel<false, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(scan_topk_kernel<false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(scan_topk_kernel<true, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(scan_topk_kernel<false, 1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    auto opt_in = [&](auto kern) {
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    };
+    opt_in(scan_topk_kernel<false, 1, false, false>);
+    opt_in(scan_topk_kernel<true, 1, false, false>);
+    opt_in(scan_topk_kernel<false, 2, false, false>);
+    opt_in(scan_topk_kernel<false, 1, true, false>);
+    opt_in(scan_topk_kernel<true, 1, true, false>);
+    opt_in(scan_topk_kernel<false, 1, true, true>);
+    opt_in(scan_topk_kernel<false, 1, false, true>);
+    opt_in(scan_topk_kernel<false, 1, false, false, true>);
+    opt_in(scan_topk_kernel<false, 2, false, false, true>);
+    opt_in(scan_topk_kernel<false, 1, true, false, true>);
+    opt_in(scan_topk_kernel<false, 1, true, true, true>);
+    opt_in(scan_topk_kernel<false, 1, false, true, true>);
     {
-        const char* nc = getenv("MPR_NO_CLUSTER");
-        if (nc && nc[0] == '1') h->use_cluster = 0;
+        auto flag = [](const char* name) { const char* v = getenv(name); return v && v[0] == '1'; };
+        if (flag("MPR_NO_CLUSTER")) h->use_cluster = 0;
         const char* cc = getenv("MPR_CAND_CAP");
         if (cc) h->cand_cap_override = atoi(cc);
         const char* eg = getenv("MPR_EPI_GROUPS");
-        if (eg && eg[0] == '1') h->epi_groups = 1;
+        if (eg && (eg[0] == '1' || eg[0] == '2')) h->epi_groups = eg[0] - '0';
         const char* ss = getenv("MPR_STAGE_SUBS");
         if (ss && (ss[0] == '1' || ss[0] == '2' || ss[0] == '4')) h->stage_subs = ss[0] - '0';
-        const char* nq = getenv("MPR_NO_QTMEM");
-        if (nq && nq[0] == '1') h->use_q_tmem = 0;
+        if (flag("MPR_NO_QTMEM")) h->use_q_tmem = 0;
+        if (flag("MPR_STATIC_TILES")) h->dynamic_tiles = 0;
+        if (flag("MPR_NO_GTHR")) h->shared_thr = 0;
+        if (flag("MPR_NO_FUSED_TAIL")) h->fused_tail = 0;
+        if (flag("MPR_NO_COOP")) h->cooperative = 0;
+        if (flag("MPR_NO_REGLIST")) h->use_reg_list = 0;
+        const char* dc = getenv("MPR_DEBUG_COUNTERS");
+        h->dbg_counters = dc && dc[0] == '1';
+        if (dc && (dc[0] == '1' || dc[0] == '2') && e == cudaSuccess) {
+            e = cudaMalloc(&h->d_dbg, kDbgWords * sizeof(unsigned long long));
+            if (e == cudaSuccess) e = cudaMemset(h->d_dbg, 0, kDbgWords * sizeof(unsigned long long));
+        }
+        const char* xt = getenv("MPR_XCHG_TIMEOUT_S");
+        if (xt && atof(xt) > 0) h->xchg_timeout_ns = static_cast<unsigned long long>(atof(xt) * 1e9);
     }
     if (e != cudaSuccess) {
         fail(nullptr, MPR_ECUDA, "handle setup failed: %s", cudaGetErrorString(e));
@@ -308,8 +515,15 @@ int mpr_create(int device, mpr_handle_t* out) {
     return MPR_OK;
 }
 
+int mpr_set_exchange_timeout(mpr_handle_t h, double seconds) {
+    if (!h || !(seconds > 0)) return fail(h, MPR_EINVAL, "timeout must be positive");
+    h->xchg_timeout_ns = static_cast<unsigned long long>(seconds * 1e9);
+    return MPR_OK;
+}
+
 int mpr_profile_begin(mpr_handle_t h, int max_launches) {
     if (!h || max_launches < 1) return fail(h, MPR_EINVAL, "bad arguments");
+    DeviceGuard guard(h->device);
     while (static_cast<int>(h->prof_events.size()) < 2 * max_launches) {
         cudaEvent_t e;
         CUDA_TRY(h, cudaEventCreate(&e));
@@ -321,6 +535,7 @@ int mpr_profile_begin(mpr_handle_t h, int max_launches) {
 
 int mpr_profile_end(mpr_handle_t h, float* total_ms, int* n_launches) {
     if (!h || !total_ms || !n_launches) return fail(h, MPR_EINVAL, "null argument");
+    DeviceGuard guard(h->device);
     const int n = h->prof_used < 0 ? 0 : h->prof_used;
     h->prof_used = -1;
     float total = 0.f;
@@ -344,16 +559,42 @@ int mpr_profile_launch_ms(mpr_handle_t h, int i, float* ms) {
 
 int mpr_destroy(mpr_handle_t h) {
     if (!h) return MPR_OK;
+    DeviceGuard guard(h->device);
     for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
     if (h->d_err) cudaFree(h->d_err);
+    if (h->d_dbg) cudaFree(h->d_dbg);
     delete h;
+    return MPR_OK;
+}
+
+int mpr_debug_counters(mpr_handle_t h, uint64_t* out8) {
+    if (!h || !out8) return fail(h, MPR_EINVAL, "null argument");
+    memset(out8, 0, 8 * sizeof(uint64_t));
+    if (!h->d_dbg) return MPR_OK;
+    DeviceGuard guard(h->device);
+    CUDA_TRY(h, cudaMemcpy(out8, h->d_dbg, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    CUDA_TRY(h, cudaMemset(h->d_dbg, 0, 8 * sizeof(uint64_t)));
+    return MPR_OK;
+}
+
+int mpr_debug_timeline(mpr_handle_t h, uint64_t* out, int n_ctas) {
+    if (!h || !out || n_ctas < 1 || n_ctas > 2048) return fail(h, MPR_EINVAL, "bad argument");
+    memset(out, 0, sizeof(uint64_t) * 16 * n_ctas);
+    if (!h->d_dbg) return MPR_OK;
+    DeviceGuard guard(h->device);
+    CUDA_TRY(h, cudaMemcpy(out, h->d_dbg + 8, sizeof(uint64_t) * 16 * n_ctas, cudaMemcpyDeviceToHost));
     return MPR_OK;
 }
 
 int mpr_device_error(mpr_handle_t h, int* code) {
     if (!h || !code) return fail(h, MPR_EINVAL, "null argument");
+    DeviceGuard guard(h->device);
     CUDA_TRY(h, cudaMemcpy(code, h->d_err, sizeof(int), cudaMemcpyDeviceToHost));
-    if (*code != 0) CUDA_TRY(h, cudaMemset(h->d_err, 0, sizeof(int)));
+    if (*code != 0) {
+        CUDA_TRY(h, cudaMemset(h->d_err, 0, sizeof(int)));
+        h->ws_ptr = nullptr;          // a starved pipeline may have left the workspace control words dirty
+        h->ws_zeroed = 0;
+    }
     return MPR_OK;
 }
 
@@ -369,6 +610,7 @@ int mpr_bank_build(mpr_handle_t h, const void* src0, int d0, const void* src1, i
     if (src_dtype < MPR_SRC_F32 || src_dtype > MPR_SRC_BF16) return fail(h, MPR_EINVAL, "bad src_dtype %d", src_dtype);
     if (!aligned16(src0) || !aligned16(src1) || !aligned16(out_bf16))
         return fail(h, MPR_EINVAL, "pointers must be 16-byte aligned");
+    DeviceGuard guard(h->device);
     const int threads = 256, rows_per_block = threads / 32;
     long long blocks = (n + rows_per_block - 1) / rows_per_block;
     const long long cap = static_cast<long long>(h->num_sms) * 16;   // grid-stride over rows beyond this
@@ -383,7 +625,7 @@ size_t mpr_search_workspace_bytes(mpr_handle_t h, int b, int64_t n_local, int d,
     if (!h) return 0;
     ScanPlan pl;
     if (make_plan(h, b, n_local, d, kk, &pl)) return 0;
-    return static_cast<size_t>(pl.n_splits) * kEpiGroups * b * kk * sizeof(uint64_t);
+    return ws_layout(pl, b, kk).total;
 }
 
 int mpr_search_plan(mpr_handle_t h, int b, int64_t n_local, int d, int kk, int* n_ctas, int* n_splits, int* n_qtiles,
@@ -400,34 +642,65 @@ int mpr_search_plan(mpr_handle_t h, int b, int64_t n_local, int d, int kk, int* 
     return MPR_OK;
 }
 
+int mpr_last_launch_count(mpr_handle_t h) { return h ? h->last_launches : 0; }
+
+int mpr_retrieve(mpr_handle_t h, const mpr_retrieve_args* a, void* stream) {
+    if (!h) return fail(nullptr, MPR_EINVAL, "null handle");
+    int rc = validate_retrieve(h, a);
+    if (rc) return rc;
+    if (a->b == 0) return MPR_OK;
+    DeviceGuard guard(h->device);
+    return run_step<false>(h, *a, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int mpr_retrieve_host(mpr_handle_t h, const mpr_retrieve_args* a, const mpr_host_io* io, void* stream) {
+    if (!h) return fail(nullptr, MPR_EINVAL, "null handle");
+    if (!io) return fail(h, MPR_EINVAL, "null io block");
+    int rc = validate_retrieve(h, a);
+    if (rc) return rc;
+    if (a->b == 0) return MPR_OK;
+    DeviceGuard guard(h->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    static const size_t kElem[3] = {4, 2, 2};
+    if (io->h_q0) {
+        if (!a->q0) return fail(h, MPR_EINVAL, "h_q0 given but a->q0 (device staging) is null");
+        CUDA_TRY(h, cudaMemcpyAsync(const_cast<void*>(a->q0), io->h_q0, static_cast<size_t>(a->b) * a->d0 * kElem[a->q_dtype],
+                                    cudaMemcpyHostToDevice, st));
+        if (io->h_q1 && a->q1)
+            CUDA_TRY(h, cudaMemcpyAsync(const_cast<void*>(a->q1), io->h_q1, static_cast<size_t>(a->b) * a->d1 * kElem[a->q_dtype],
+                                        cudaMemcpyHostToDevice, st));
+    }
+    if (io->h_prefix_ids && a->answer_id) {
+        if (!io->h_prefix_off) return fail(h, MPR_EINVAL, "h_prefix_off is null");
+        if (io->n_prefix_ids > 0)
+            CUDA_TRY(h, cudaMemcpyAsync(const_cast<int32_t*>(a->prefix_ids), io->h_prefix_ids,
+                                        sizeof(int32_t) * static_cast<size_t>(io->n_prefix_ids), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(h, cudaMemcpyAsync(const_cast<int32_t*>(a->prefix_off), io->h_prefix_off,
+                                    sizeof(int32_t) * (static_cast<size_t>(a->b) + 1), cudaMemcpyHostToDevice, st));
+    }
+    rc = run_step<false>(h, *a, nullptr, st);
+    if (rc) return rc;
+    if (io->h_out && io->d_out && io->out_bytes)
+        CUDA_TRY(h, cudaMemcpyAsync(io->h_out, io->d_out, io->out_bytes, cudaMemcpyDeviceToHost, st));
+    if (io->sync) CUDA_TRY(h, cudaStreamSynchronize(st));
+    return MPR_OK;
+}
+
 int mpr_search_topk(mpr_handle_t h, const uint16_t* q, int b, const uint16_t* bank, const float* bias, int64_t n_local,
                     int64_t idx_base, int d, int kk, uint64_t* out_keys, float* out_score, int32_t* out_idx,
                     void* workspace, size_t workspace_bytes, void* stream) {
     if (!h) return fail(nullptr, MPR_EINVAL, "null handle");
     if (b == 0) return MPR_OK;
-    if (!q || !bank || !bias || !workspace) return fail(h, MPR_EINVAL, "null pointer");
-    if (!aligned16(q) || !aligned16(bank) || !aligned16(workspace))
-        return fail(h, MPR_EINVAL, "q, bank and workspace must be 16-byte aligned");
-    if (idx_base < 0 || idx_base + n_local >= 0xFFFFFFFFll) return fail(h, MPR_EINVAL, "global row index exceeds 32 bits");
-    ScanPlan pl;
-    int rc = make_plan(h, b, n_local, d, kk, &pl);
-    if (rc) return rc;
-    const size_t need = static_cast<size_t>(pl.n_splits) * kEpiGroups * b * kk * sizeof(uint64_t);
-    if (workspace_bytes < need)
-        return fail(h, MPR_EWORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, need);
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    uint64_t* part = static_cast<uint64_t*>(workspace);
-    rc = launch_scan<false>(h, pl, q, b, bank, bias, n_local, idx_base, d, kk, part, nullptr, st);
-    if (rc) return rc;
-    const int warps_per_block = 4;
-    merge_topk_kernel<<<(b + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(
-        part, pl.n_splits * kEpiGroups, 1ll, static_cast<long long>(kk) * pl.n_splits * kEpiGroups,
-        static_cast<long long>(pl.n_splits) * kEpiGroups, b, kk, out_keys, out_score, out_idx);
-    CUDA_TRY(h, cudaGetLastError());
-    return MPR_OK;
+    if (!q) return fail(h, MPR_EINVAL, "null pointer");
+    mpr_retrieve_args a;
+    memset(&a, 0, sizeof(a));
+    a.q_bf16 = q; a.b = b; a.bank = bank; a.bias = bias; a.n_local = n_local; a.idx_base = idx_base; a.d = d; a.kk = kk;
+    a.out_keys = out_keys; a.out_score = out_score; a.out_idx = out_idx;
+    a.workspace = workspace; a.workspace_bytes = workspace_bytes;
+    return mpr_retrieve(h, &a, stream);
 }
 
-int mpr_search_fused_supported(mpr_handle_t h, int d) { return h && h->use_q_tmem && d >= 64 && d <= 512 && d % 64 == 0; }
+int mpr_search_fused_supported(mpr_handle_t h, int d) { return h && d >= 64 && d <= 2048 && d % 64 == 0; }
 
 int mpr_search_topk_fused(mpr_handle_t h, const void* src0, int d0, const void* src1, int d1, int src_dtype,
                           int normalise, int b, const uint16_t* bank, const float* bias, int64_t n_local,
@@ -435,34 +708,17 @@ int mpr_search_topk_fused(mpr_handle_t h, const void* src0, int d0, const void* 
                           float* out_q_bias, void* workspace, size_t workspace_bytes, void* stream) {
     if (!h) return fail(nullptr, MPR_EINVAL, "null handle");
     if (b == 0) return MPR_OK;
+    if (!src0) return fail(h, MPR_EINVAL, "null pointer");
     if (!src1) d1 = 0;
-    const int d = d0 + d1;
-    if (!src0 || !bank || !bias || !workspace) return fail(h, MPR_EINVAL, "null pointer");
-    if (d0 < 8 || d0 % 8 || d1 % 8) return fail(h, MPR_EINVAL, "query halves must be multiples of 8 wide (d0=%d d1=%d)", d0, d1);
-    if (!mpr_search_fused_supported(h, d))
-        return fail(h, MPR_EINVAL, "fused query preparation needs the tensor-memory q-tile (64 <= D <= 512, D %% 64 == 0); got D=%d", d);
-    if (src_dtype < MPR_SRC_F32 || src_dtype > MPR_SRC_BF16) return fail(h, MPR_EINVAL, "bad src_dtype %d", src_dtype);
-    if (!aligned16(src0) || !aligned16(src1) || !aligned16(bank) || !aligned16(workspace))
-        return fail(h, MPR_EINVAL, "pointers must be 16-byte aligned");
-    if (idx_base < 0 || idx_base + n_local >= 0xFFFFFFFFll) return fail(h, MPR_EINVAL, "global row index exceeds 32 bits");
-    ScanPlan pl;
-    int rc = make_plan(h, b, n_local, d, kk, &pl);
-    if (rc) return rc;
-    const size_t need = static_cast<size_t>(pl.n_splits) * kEpiGroups * b * kk * sizeof(uint64_t);
-    if (workspace_bytes < need) return fail(h, MPR_EWORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, need);
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    uint64_t* part = static_cast<uint64_t*>(workspace);
-    FusedQ fq;
-    fq.src0 = src0; fq.src1 = src1; fq.d0 = d0; fq.d1 = d1; fq.dtype = src_dtype; fq.normalise = normalise;
-    fq.q_bias_out = out_q_bias;
-    rc = launch_scan<false>(h, pl, nullptr, b, bank, bias, n_local, idx_base, d, kk, part, nullptr, st, fq);
-    if (rc) return rc;
-    const int warps_per_block = 4;
-    merge_topk_kernel<<<(b + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(
-        part, pl.n_splits * kEpiGroups, 1ll, static_cast<long long>(kk) * pl.n_splits * kEpiGroups,
-        static_cast<long long>(pl.n_splits) * kEpiGroups, b, kk, out_keys, out_score, out_idx);
-    CUDA_TRY(h, cudaGetLastError());
-    return MPR_OK;
+    if (!mpr_search_fused_supported(h, d0 + d1))
+        return fail(h, MPR_EINVAL, "fused query preparation needs 64 <= D <= 2048, D %% 64 == 0; got D=%d", d0 + d1);
+    mpr_retrieve_args a;
+    memset(&a, 0, sizeof(a));
+    a.q0 = src0; a.q1 = src1; a.d0 = d0; a.d1 = d1; a.q_dtype = src_dtype; a.normalise = normalise;
+    a.b = b; a.bank = bank; a.bias = bias; a.n_local = n_local; a.idx_base = idx_base; a.d = d0 + d1; a.kk = kk;
+    a.out_keys = out_keys; a.out_score = out_score; a.out_idx = out_idx; a.out_q_bias = out_q_bias;
+    a.workspace = workspace; a.workspace_bytes = workspace_bytes;
+    return mpr_retrieve(h, &a, stream);
 }
 
 int mpr_merge_topk(mpr_handle_t h, const uint64_t* in_keys, int n_lists, int b, int kk, uint64_t* out_keys,
@@ -471,6 +727,7 @@ int mpr_merge_topk(mpr_handle_t h, const uint64_t* in_keys, int n_lists, int b, 
     if (b == 0) return MPR_OK;
     if (!in_keys || n_lists < 1 || b < 0) return fail(h, MPR_EINVAL, "bad arguments");
     if (kk < 1 || kk > MPR_MAX_KK) return fail(h, MPR_EINVAL, "k + skip must be in [1, %d] (got %d)", MPR_MAX_KK, kk);
+    DeviceGuard guard(h->device);
     const int warps_per_block = 4;
     merge_topk_kernel<<<(b + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0,
                         static_cast<cudaStream_t>(stream)>>>(in_keys, n_lists, static_cast<long long>(b) * kk,
@@ -483,38 +740,6 @@ int mpr_merge_topk(mpr_handle_t h, const uint64_t* in_keys, int n_lists, int b, 
 size_t mpr_exchange_bytes(int world, int cap) {
     if (world < 1 || world > kXchgMaxWorld || cap < 1) return 0;
     return xchg_bytes(world, cap);
-}
-
-int mpr_exchange_push(mpr_handle_t h, const uint64_t* local_keys, int b, int kk, int rank, int world,
-                      void* const* peer_bufs, int cap, void* stream) {
-    if (!h) return fail(nullptr, MPR_EINVAL, "null handle");
-    if (!local_keys || !peer_bufs) return fail(h, MPR_EINVAL, "null pointer");
-    if (world < 1 || world > kXchgMaxWorld || rank < 0 || rank >= world)
-        return fail(h, MPR_EINVAL, "bad rank/world %d/%d (max world %d)", rank, world, kXchgMaxWorld);
-    if (b < 1 || kk < 1 || kk > MPR_MAX_KK || static_cast<long long>(b) * kk > cap)
-        return fail(h, MPR_EINVAL, "b*kk = %lld exceeds the exchange capacity %d", static_cast<long long>(b) * kk, cap);
-    XchgPeers peers;
-    for (int r = 0; r < kXchgMaxWorld; ++r) peers.buf[r] = r < world ? static_cast<unsigned char*>(peer_bufs[r]) : nullptr;
-    for (int r = 0; r < world; ++r)
-        if (!peers.buf[r] || !aligned16(peers.buf[r])) return fail(h, MPR_EINVAL, "peer buffer %d is null or unaligned", r);
-    xchg_push_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(local_keys, b * kk, rank, world, cap, peers);
-    CUDA_TRY(h, cudaGetLastError());
-    return MPR_OK;
-}
-
-int mpr_exchange_merge(mpr_handle_t h, void* my_buf, int world, int cap, int b, int kk, uint64_t* out_keys,
-                       float* out_score, int32_t* out_idx, void* stream) {
-    if (!h) return fail(nullptr, MPR_EINVAL, "null handle");
-    if (!my_buf || !aligned16(my_buf)) return fail(h, MPR_EINVAL, "exchange buffer is null or unaligned");
-    if (world < 1 || world > kXchgMaxWorld) return fail(h, MPR_EINVAL, "bad world %d", world);
-    if (b < 1 || kk < 1 || kk > MPR_MAX_KK || static_cast<long long>(b) * kk > cap)
-        return fail(h, MPR_EINVAL, "b*kk = %lld exceeds the exchange capacity %d", static_cast<long long>(b) * kk, cap);
-    const int warps_per_block = 4;
-    xchg_merge_kernel<<<(b + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0,
-                        static_cast<cudaStream_t>(stream)>>>(static_cast<unsigned char*>(my_buf), world, cap, b, kk,
-                                                             out_keys, out_score, out_idx, h->d_err);
-    CUDA_TRY(h, cudaGetLastError());
-    return MPR_OK;
 }
 
 int mpr_prompt_gather(mpr_handle_t h, const int32_t* idx, int b, int kk, int skip, const int32_t* answer_id,
@@ -530,6 +755,7 @@ int mpr_prompt_gather(mpr_handle_t h, const int32_t* idx, int b, int kk, int ski
     if (kk < 1 || kk > MPR_MAX_KK || skip < 0 || skip >= kk)
         return fail(h, MPR_EINVAL, "need 1 <= kk <= %d and 0 <= skip < kk (kk=%d skip=%d)", MPR_MAX_KK, kk, skip);
     if (max_len < 1 || out_stride < 1) return fail(h, MPR_EINVAL, "max_len and out_stride must be >= 1");
+    DeviceGuard guard(h->device);
     PromptParams p;
     p.idx = idx; p.b = b; p.kk = kk; p.skip = skip;
     p.answer_id = answer_id; p.bucket_lut = bucket_lut;
@@ -547,17 +773,48 @@ int mpr_prompt_gather(mpr_handle_t h, const int32_t* idx, int b, int kk, int ski
     return MPR_OK;
 }
 
+int mpr_embed_prompt(mpr_handle_t h, const int64_t* input_ids, const int64_t* attention_mask, int b, int len, int in_stride,
+                     const void* table, int table_dtype, int vocab, int hidden, const void* image_tokens, int n_image,
+                     void* out_embeds, void* out_mask, int mask_f32, void* stream) {
+    if (!h) return fail(nullptr, MPR_EINVAL, "null handle");
+    if (b == 0) return MPR_OK;
+    if (!input_ids || !attention_mask || !table || !out_embeds || !out_mask) return fail(h, MPR_EINVAL, "null pointer");
+    if (b < 0 || len < 1 || in_stride < len || vocab < 1 || n_image < 0 || (n_image > 0 && !image_tokens))
+        return fail(h, MPR_EINVAL, "bad shape (b=%d len=%d in_stride=%d vocab=%d n_image=%d)", b, len, in_stride, vocab, n_image);
+    if (table_dtype < MPR_SRC_F32 || table_dtype > MPR_SRC_BF16) return fail(h, MPR_EINVAL, "bad table_dtype %d", table_dtype);
+    const int esize = table_dtype == MPR_SRC_F32 ? 4 : 2;
+    if (hidden < 1 || (hidden * esize) % 16 != 0) return fail(h, MPR_EINVAL, "hidden * element size must be a multiple of 16 bytes");
+    if (!aligned16(table) || !aligned16(out_embeds) || !aligned16(image_tokens))
+        return fail(h, MPR_EINVAL, "table, image_tokens and out_embeds must be 16-byte aligned");
+    DeviceGuard guard(h->device);
+    EmbedParams p;
+    p.input_ids = reinterpret_cast<const long long*>(input_ids);
+    p.attention_mask = reinterpret_cast<const long long*>(attention_mask);
+    p.b = b; p.len = len; p.in_stride = in_stride;
+    p.table = static_cast<const uint4*>(table); p.vocab = vocab; p.row_vec = hidden * esize / 16;
+    p.image_tokens = static_cast<const uint4*>(image_tokens); p.n_image = n_image;
+    p.out = static_cast<uint4*>(out_embeds); p.out_mask = out_mask; p.mask_f32 = mask_f32;
+    p.err = h->d_err;
+    const long long rows = static_cast<long long>(b) * (n_image + len);
+    const int warps_per_block = 8;
+    long long blocks = (rows + warps_per_block - 1) / warps_per_block;
+    const long long cap = static_cast<long long>(h->num_sms) * 8;
+    if (blocks > cap) blocks = cap;
+    embed_prompt_kernel<<<static_cast<unsigned>(blocks), warps_per_block * 32, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    CUDA_TRY(h, cudaGetLastError());
+    return MPR_OK;
+}
+
 int mpr_debug_scores(mpr_handle_t h, const uint16_t* q, int b, const uint16_t* bank, const float* bias,
                      int64_t n_local, int d, float* scores, void* workspace, size_t workspace_bytes, void* stream) {
     if (!h) return fail(nullptr, MPR_EINVAL, "null handle");
     if (!q || !bank || !bias || !scores || !workspace) return fail(h, MPR_EINVAL, "null pointer");
-    ScanPlan pl;
-    int rc = make_plan(h, b, n_local, d, 1, &pl);
-    if (rc) return rc;
-    const size_t need = static_cast<size_t>(pl.n_splits) * kEpiGroups * b * sizeof(uint64_t);
-    if (workspace_bytes < need) return fail(h, MPR_EWORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, need);
-    return launch_scan<true>(h, pl, q, b, bank, bias, n_local, 0, d, 1, static_cast<uint64_t*>(workspace), scores,
-                             static_cast<cudaStream_t>(stream));
+    DeviceGuard guard(h->device);
+    mpr_retrieve_args a;
+    memset(&a, 0, sizeof(a));
+    a.q_bf16 = q; a.b = b; a.bank = bank; a.bias = bias; a.n_local = n_local; a.d = d; a.kk = 1;
+    a.workspace = workspace; a.workspace_bytes = workspace_bytes;
+    return run_step<true>(h, a, scores, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -32,7 +32,15 @@ __device__ __forceinline__ bool elect_one() {
 
 __device__ __forceinline__ uint64_t globaltimer_ns() {
     uint64_t t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t) :: "memory");
+    return t;
+}
+
+// The same behind a call boundary: ptxas is free to hoist a special-register read above a bar.sync (it is not a memory
+// operation); a non-inlined call is not reordered across barriers.  Debug timeline only.
+__device__ __noinline__ uint64_t globaltimer_ns_fenced() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t) :: "memory");
     return t;
 }
 

@@ -1,23 +1,31 @@
 // Kernel 2 — fused bank scan: bf16 similarity GEMM on tcgen05 (accumulators in TMEM, operands staged by
-// TMA through an mbarrier ring) whose epilogue keeps a streaming per-query top-k.  The [B, N] score matrix
-// of the reference (torch.cdist -> torch.argsort, /root/reference/dataset/VQAFeatureDataset.py:192-197)
-// is never written.
+// TMA through an mbarrier ring) whose epilogue keeps a streaming per-query top-k, and whose tail — when the grid is a
+// single wave — finishes the whole retrieval step in the same launch (tail.cuh).  The [B, N] score matrix of the
+// reference (torch.cdist -> torch.argsort, /root/reference/dataset/VQAFeatureDataset.py:192-197) is never written.
 //
 // score[q, r] = <q, bank[r]> + bias[r],  bias[r] = -0.5 * ||bank[r]||^2   (so argmax score == argmin L2 distance)
 //
 // Orientation: queries are the MMA M dimension (one TMEM lane per query), bank rows the N dimension
 // (one TMEM column per row).  Each epilogue thread therefore owns ONE query and walks its lane's columns in
 // ascending row order: the common case per score is one FADD + a share of a max and a vote; only scores that
-// beat the query's current k-th best are appended to a thread-private pending buffer and folded in later.
+// beat the query's current admission threshold are appended to a thread-private pending buffer and folded in later.
 //
-// Work decomposition: item = (bank split s, q-tile t); one CTA per item, blockIdx.x = s * n_qtiles + t, so the
-// CTAs resident at the same time share a bank range and all but the first read of it hit L2.  The q-tile
-// (<= 128 queries, <= 128 KiB) is loaded once and stays resident (tensor memory for D <= 512, else shared memory);
-// only the bank streams.
+// Work decomposition: the CTAs of one q-tile (<= 128 queries, loaded once, resident in tensor memory for D <= 512, else
+// in shared memory) pull 128-row bank tiles from a shared atomic counter (dynamic scheduling: HBM speed differs by a
+// few percent between SMs, a static split leaves the fast ones idle at the end); blockIdx.x = s * n_qtiles + t, so the
+// CTAs resident at the same time walk the bank together and all but the first read of a tile hit L2.
 //
-// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected lane),
-// warps 2..9 = two epilogue groups of four warps (warp w reads TMEM lanes 32*(w%4)...); group g takes tiles g, g+2, ...
-// and keeps its own per-query lists, so a tile's epilogue may take two MMA tile-times before it stalls the pipe.
+// Shared admission thresholds: every (CTA, epilogue group) list publishes its best score with atomicMax into one of
+// ns >= kk slots per query (slot = list id mod ns).  The lists cover disjoint rows, so the MINIMUM over a query's ns
+// slots is a lower bound on its global kk-th best score: ns distinct rows are known to score at least that much, and
+// anything strictly below it can be dropped by every CTA without ever entering a list.  After the first tile this
+// replaces each CTA's slowly converging private threshold (k-th best of ITS rows) by a near-global one, which is what
+// keeps list maintenance off the critical path for large k and for small per-GPU shards.
+//
+// Warp roles (320 threads): warp 0 = TMA producer + tile scheduler, warp 1 = TMEM allocator + MMA issuer (one elected
+// lane), warps 2..9 = two epilogue groups of four warps (warp w reads TMEM lanes 32*(w%4)...); group g takes this CTA's
+// tiles g, g+2, ... and keeps its own per-query lists, so a tile's epilogue may take two MMA tile-times before it stalls
+// the pipe.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -26,6 +34,7 @@
 
 #include "bank_build.cuh"
 #include "ptx.cuh"
+#include "tail.cuh"
 #include "topk_key.cuh"
 
 namespace mpr {
@@ -37,12 +46,15 @@ constexpr int kStageBytes = kTileRows * 128;  // one bank K-chunk: 128 rows x 12
 constexpr int kAccBufs = 4;                   // TMEM accumulator ring: 4 x 128 columns (2 when the q-tile is in TMEM)
 constexpr int kTmemCols = 512;
 constexpr int kScanThreads = 320;            // warp 0 TMA, warp 1 MMA, warps 2..9 = two epilogue groups of four
+constexpr int kScanWarps = kScanThreads / 32;
 constexpr int kMaxStages = 12;
 constexpr int kMaxSmem = 232448;              // 227 KiB opt-in limit per CTA on sm_100
 constexpr int kMaxKK = 32;
 constexpr int kMaxSubPerStage = 4;           // 64-wide K sub-chunks per ring stage
 constexpr int kEpiGroups = 2;                 // epilogue groups; group g owns tiles g, g+2, ... (own lists per query)
 constexpr int kCandCapMax = 16;               // per-query pending-candidate slots (a flush leaves >= 8 free)
+constexpr int kTileRing = 64;                 // scheduler -> consumers tile-id ring (entries); >= the producer's lead
+constexpr uint32_t kTileEnd = 0xFFFFFFFFu;
 
 struct ScanParams {
     int b_total;       // queries in the batch
@@ -54,7 +66,7 @@ struct ScanParams {
     int q_tile;        // queries per q-tile
     int q_box_rows;    // rows of the Q TMA box (multiple of 8, >= valid rows of any q-tile)
     int n_qtiles;
-    int n_splits;
+    int n_splits;      // CTAs per q-tile
     int n_tiles;       // ceil(n_local / 128)
     int n_stages;
     int n_epi_groups;  // epilogue groups actually used (1 or 2)
@@ -65,18 +77,25 @@ struct ScanParams {
     const uint16_t* q;     // [b_total][d] bf16 queries (read directly in the TMEM-operand variant)
     int d;                 // row length
     // fused query preparation (kFuseQ): the raw CLIP halves are concatenated, optionally normalised and rounded to bf16
-    // on their way into tensor memory — no separate cast kernel, no bf16 copy of the queries in HBM
+    // on their way into tensor / shared memory — no separate cast kernel, no bf16 copy of the queries in HBM
     const void* qsrc0;     // [b_total][qd0]
     const void* qsrc1;     // [b_total][qd1] or nullptr
     int qd0, qd1, q_dtype, q_normalise;
     float* q_bias_out;     // [b_total] -0.5*|bf16(q)|^2 (written by split 0), or nullptr
     uint64_t* part_keys;   // [b_total][kk][n_splits * kEpiGroups]
+    uint32_t* tile_ctr;    // [n_qtiles] dynamic tile scheduler (nullptr: static contiguous ranges)
+    uint32_t* gthr;        // [b_total][ns] shared admission thresholds, ordered-u32 scores (nullptr: off)
+    int ns;                // threshold slots per query (multiple of 4, >= kk)
+    int fused_tail;        // 1: grid barrier + tail.cuh in this launch (grid must be co-resident)
+    unsigned long long* dbg;  // debug counters (MPR_DEBUG_COUNTERS=1) or nullptr: [0] candidates admitted, [1] warp flushes,
+                           // [2] slow-path 8-groups (per warp), [3] list replacements, [4] warp-tiles, [5] threshold refreshes that found a bound
+    unsigned long long* dbg_ts;  // debug timeline (MPR_DEBUG_COUNTERS=1|2) or nullptr: [16 * cta + event]
     float* dump;           // debug: [b_total][n_local] scores, or nullptr
     int* err;              // device word that receives the code of a starved barrier
 };
 
 struct ScanSmemLayout {
-    uint32_t q_off, stage_off, list_off, bias_off, bar_off, total;
+    uint32_t q_off, stage_off, list_off, bias_off, ring_off, scr_off, bar_off, total;
 };
 
 // Per-query shared-memory row: [kk_pad sorted keys | cand_cap pending candidates | pad]; the odd stride (in
@@ -92,30 +111,83 @@ __host__ __device__ inline ScanSmemLayout scan_smem_layout(int n_chunks, int q_b
     l.stage_off = static_cast<uint32_t>(n_chunks) * q_box_rows * 128u;          // multiple of 1024
     l.list_off = l.stage_off + static_cast<uint32_t>(n_stages) * sub_per_stage * kStageBytes;
     l.bias_off = l.list_off + static_cast<uint32_t>(n_groups * kUmmaM) * scan_row_stride(kk_pad, cand_cap) * 8u;
-    l.bar_off = l.bias_off + kAccBufs * kTileRows * 4u;
+    l.ring_off = l.bias_off + kAccBufs * kTileRows * 4u;
+    l.scr_off = l.ring_off + kTileRing * 8u;
+    l.bar_off = l.scr_off + 2 * kUmmaM * 4u;
     l.total = l.bar_off + (1 + 2 * kMaxStages + 2 * kAccBufs) * 8u + 16u;
     return l;
 }
 
 // Barrier error codes (ScanParams::err)
-enum : int { kErrQFull = 101, kErrEmpty = 102, kErrFull = 103, kErrTmemEmpty = 104, kErrTmemFull = 105 };
+enum : int { kErrQFull = 101, kErrEmpty = 102, kErrFull = 103, kErrTmemEmpty = 104, kErrTmemFull = 105, kErrRing = 106,
+             kErrGridBarrier = 107 };
+
+// One row of the query batch: concat + (normalise) + bf16 rounding exactly as kernel 1 does it (same per-lane
+// accumulation order and the same warp reduction, so `-0.5 * sum` equals kernel 1's bias bit for bit), written as 16-byte
+// units into a K-major SWIZZLE_128B shared-memory q-tile (slab j = K-chunk j, row r at r*128, unit c at (c ^ (r&7))*16).
+__device__ __forceinline__ float prep_query_row_to_smem(const ScanParams& p, long long src_row, bool real, uint8_t* q_tile,
+                                                        uint32_t slab_bytes, int r, int lane) {
+    const int steps = (p.d + 255) / 256;
+    float x[kBuildMaxSteps][8];
+    float ss = 0.f;
+#pragma unroll
+    for (int s = 0; s < kBuildMaxSteps; ++s) {
+        const int col = s * 256 + lane * 8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[s][i] = 0.f;
+        if (s < steps && col < p.d && real) {
+            if (col < p.qd0) load8(p.qsrc0, p.q_dtype, static_cast<size_t>(src_row) * p.qd0 + col, x[s]);
+            else             load8(p.qsrc1, p.q_dtype, static_cast<size_t>(src_row) * p.qd1 + (col - p.qd0), x[s]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) ss = fmaf(x[s][i], x[s][i], ss);
+        }
+    }
+    float scale = 1.f;
+    if (p.q_normalise) {
+        ss = warp_sum(ss);
+        scale = ss > 0.f ? 1.0f / sqrtf(ss) : 0.f;
+    }
+    float rs = 0.f;
+#pragma unroll
+    for (int s = 0; s < kBuildMaxSteps; ++s) {
+        const int col = s * 256 + lane * 8;
+        if (s < steps && col < p.d) {
+            uint32_t packed[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const __nv_bfloat16 lo = __float2bfloat16_rn(x[s][2 * i] * scale);
+                const __nv_bfloat16 hi = __float2bfloat16_rn(x[s][2 * i + 1] * scale);
+                const float flo = __bfloat162float(lo), fhi = __bfloat162float(hi);
+                rs = fmaf(flo, flo, rs);
+                rs = fmaf(fhi, fhi, rs);
+                packed[i] = static_cast<uint32_t>(__bfloat16_as_ushort(lo)) |
+                            (static_cast<uint32_t>(__bfloat16_as_ushort(hi)) << 16);
+            }
+            const int unit = col >> 3, j = unit >> 3, c = unit & 7;
+            *reinterpret_cast<uint4*>(q_tile + static_cast<size_t>(j) * slab_bytes + r * 128 + ((c ^ (r & 7)) << 4)) =
+                make_uint4(packed[0], packed[1], packed[2], packed[3]);
+        }
+    }
+    return warp_sum(rs);
+}
 
 // kCluster = 2 (shared-memory q-tile variant, even number of q-tiles): the two CTAs of a cluster work on the SAME bank
 // split with DIFFERENT q-tiles; each loads half of every bank K-chunk and TMA-multicasts it into both CTAs' rings, which
 // halves the L2 reads per MMA.  A ring slot is refilled only after BOTH consumers have released it (multicast
-// tcgen05.commit, empty count = 2).  Measured effect at B = 4096: +3 % — L2 bandwidth was not the limiter.
+// tcgen05.commit, empty count = 2).  Tiles are statically split in this variant (both CTAs must walk the same tiles).
 //
 // kQTmem (D <= 512): the q-tile lives in TENSOR MEMORY (columns [0, D/2)) and is the MMA's TMEM A operand.  Only B then
-// crosses the 128 B/cycle shared-memory port (an SS-mode 128x128x16 MMA alone reads 8 KiB per 64 cycles = all of it), and
-// the 128 KiB the q-tile used to occupy go to the bank ring (160+ KiB in flight instead of 64).  The accumulator ring is
-// then 2 x 128 columns at [256, 512).  On its own this moved nothing either; what actually bound the tensor regime
-// (41 % tensor-pipe activity with no warp waiting on data) was the MMA warp's own instruction stream — see the
-// warp-uniform issue loop below and the multi-sub-chunk ring stages.
-// kFuseQ (with kQTmem): see ScanParams::qsrc0 — replaces /root/reference/dataset/VQAFeatureDataset.py:189-191 in-kernel.
-template <bool kDump, int kCluster, bool kQTmem, bool kFuseQ = false>
+// crosses the 128 B/cycle shared-memory port, and the shared memory the q-tile would occupy goes to the bank ring.  The
+// accumulator ring is then 2 x 128 columns at [256, 512).
+// kRegList (k + skip <= 8, the headline k = 5): the per-query list lives in REGISTERS (8 keys, unsorted, minimum tracked):
+// an admitted score replaces the minimum with ~60 register instructions and moves the threshold at once — no pending
+// buffer, no shared-memory latency chain.  Larger k keeps the list in shared memory behind a pending buffer.
+// kFuseQ: see ScanParams::qsrc0 — replaces /root/reference/dataset/VQAFeatureDataset.py:189-191 in-kernel, for the
+// tensor-memory q-tile (each epilogue thread converts its own row) and the shared-memory one (a warp per row, D <= 2048).
+template <bool kDump, int kCluster, bool kQTmem, bool kFuseQ = false, bool kRegList = false>
 __global__ void __launch_bounds__(kScanThreads, 1)
 scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_bank,
-                 const ScanParams p) {
+                 const ScanParams p, const TailParams tail) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = ptx::smem_u32(smem_raw);
     const uint32_t base = (raw_addr + 1023u) & ~1023u;   // SWIZZLE_128B atoms need 1024-byte alignment
@@ -126,6 +198,8 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const uint32_t stage_smem = base + lay.stage_off;
     uint64_t* lists = reinterpret_cast<uint64_t*>(smem + lay.list_off);
     float* bias_s = reinterpret_cast<float*>(smem + lay.bias_off);
+    volatile uint64_t* tile_ring = reinterpret_cast<volatile uint64_t*>(smem + lay.ring_off);
+    float* scratch = reinterpret_cast<float*>(smem + lay.scr_off);
     const uint32_t bar_base = base + lay.bar_off;
     const uint32_t bar_q = bar_base;
     auto bar_full = [&](int s) { return bar_base + 8u + 8u * s; };
@@ -139,6 +213,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const int lane = threadIdx.x & 31;
     constexpr int kBufs = kQTmem ? 2 : kAccBufs;               // accumulator ring depth
     constexpr uint32_t kAccCol0 = kQTmem ? 256u : 0u;          // first accumulator column
+    constexpr bool kWarpsFillQ = kQTmem || kFuseQ;             // the epilogue warps (not TMA) bring the q-tile in
 
     // ---- which item is this CTA's
     const int item = blockIdx.x;
@@ -146,13 +221,13 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const int qt = item - split * p.n_qtiles;
     const int q0 = qt * p.q_tile;
     const int q_valid = min(p.q_tile, p.b_total - q0);
+    const bool dynamic = kCluster == 1 && p.tile_ctr != nullptr;
     const int tile_begin = static_cast<int>(static_cast<long long>(split) * p.n_tiles / p.n_splits);
     const int tile_end = static_cast<int>(static_cast<long long>(split + 1) * p.n_tiles / p.n_splits);
-    const int my_tiles = tile_end - tile_begin;
 
     // ---- one-time setup
     if (threadIdx.x == 0) {
-        ptx::mbar_init(bar_q, kQTmem ? 4 : 1);          // TMEM variant: one arrive per epilogue warp
+        ptx::mbar_init(bar_q, kWarpsFillQ ? 8 : 1);      // one arrive per epilogue warp, or the TMA producer's
         for (int s = 0; s < p.n_stages; ++s) {
             ptx::mbar_init(bar_full(s), 1);
             ptx::mbar_init(bar_empty(s), kCluster);      // one release per consumer CTA of the cluster
@@ -162,9 +237,10 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             ptx::mbar_init(bar_tempty(b), 4);   // one arrive per epilogue warp
         }
         ptx::fence_mbar_init();
-        if constexpr (!kQTmem) ptx::prefetch_tensormap(&tmap_q);
-        ptx::prefetch_tensormap(&tmap_bank);
+        if constexpr (!kWarpsFillQ) ptx::prefetch_tensormap(&tmap_q);
+        if (p.n_tiles > 0) ptx::prefetch_tensormap(&tmap_bank);
     }
+    if (threadIdx.x < kTileRing) tile_ring[threadIdx.x] = 0ull;
     if (warp == 1) {
         ptx::tmem_alloc(ptx::smem_u32(const_cast<uint32_t*>(tmem_slot)), kTmemCols);
         ptx::tmem_relinquish();
@@ -174,8 +250,33 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     if constexpr (kCluster > 1) ptx::cluster_sync();      // peers' barriers exist before anything remote touches them
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // debug timeline (MPR_DEBUG_COUNTERS=1): dbg[8 + 16*cta + k] = globaltimer at event k of this CTA
+    auto stamp = [&](int k) {
+        if (p.dbg_ts) p.dbg_ts[16 * blockIdx.x + k] = ptx::globaltimer_ns_fenced();
+    };
+    if (threadIdx.x == 0) stamp(0);
     const uint32_t crank = kCluster > 1 ? ptx::cluster_ctarank() : 0u;
     constexpr uint16_t kClusterMask = static_cast<uint16_t>((1u << kCluster) - 1u);
+
+    // Entry lt of the tile ring = ((lt + 1) << 32) | tile id, written by the producer when it starts loading this CTA's
+    // lt-th tile (kTileEnd = no more tiles).  Consumers spin on the tag; the producer can run ahead of them by at most
+    // the bank ring plus the accumulator ring (< kTileRing tiles), so an entry is never overwritten before it was read.
+    auto ring_wait = [&](int lt) -> uint32_t {
+        const uint64_t want = static_cast<uint64_t>(lt) + 1ull;
+        uint64_t e = tile_ring[lt & (kTileRing - 1)];
+        if ((e >> 32) != want) {
+            const uint64_t t0 = ptx::globaltimer_ns();
+            uint32_t polls = 0;
+            while (((e = tile_ring[lt & (kTileRing - 1)]) >> 32) != want) {
+                if ((++polls & 0x3FFu) == 0 && ptx::globaltimer_ns() - t0 > 4000000000ull) {
+                    if (p.err) atomicCAS(p.err, 0, kErrRing);
+                    __threadfence_system();
+                    __trap();
+                }
+            }
+        }
+        return static_cast<uint32_t>(e);
+    };
 
     // Producer and MMA warps run their loops with WARP-UNIFORM control flow (all 32 lanes wait on the barriers together)
     // and elect one lane only around the asynchronous instructions themselves.  Putting the whole loop under
@@ -183,8 +284,8 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     // election loop with R2UR moves (~130 SASS instructions per K-chunk, measured: MMA issue-bound at 41 % tensor
     // activity with nothing waiting on data).
     if (warp == 0) {
-        // =========================== TMA producer ===========================
-        if constexpr (!kQTmem) {
+        // =========================== TMA producer + tile scheduler ===========================
+        if constexpr (!kWarpsFillQ) {
             if (ptx::elect_one()) {
                 // resident q-tile: one 128-byte-wide slab per K-chunk
                 const uint32_t slab_bytes = static_cast<uint32_t>(p.q_box_rows) * 128u;
@@ -196,9 +297,39 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         }
         // streamed bank: a ring stage holds up to sub_per_stage 64-wide K sub-chunks and costs ONE barrier round-trip
         const int spp = p.sub_per_stage;
+        const uint32_t t_limit = dynamic ? static_cast<uint32_t>(p.n_tiles) : static_cast<uint32_t>(tile_end);
+        uint32_t t_cur;
+        if (dynamic) {
+            uint32_t g = 0;
+            if (lane == 0) g = atomicAdd(p.tile_ctr + qt, 1u);
+            t_cur = __shfl_sync(kFullMask, g, 0);
+        } else {
+            t_cur = static_cast<uint32_t>(tile_begin);
+        }
         int s = 0;
         uint32_t ph = 0;
-        for (int t = tile_begin; t < tile_end; ++t) {
+        for (int lt = 0;; ++lt) {
+            const bool have = t_cur < t_limit;
+            uint32_t t_next = t_cur + 1u;
+            if (dynamic && have && lane == 0) t_next = atomicAdd(p.tile_ctr + qt, 1u);   // consumed after the loads below
+            if (lane == 0) {
+                if (have) {
+                    tile_ring[lt & (kTileRing - 1)] = ((static_cast<uint64_t>(lt) + 1ull) << 32) | t_cur;
+                } else {
+                    for (int g = 0; g < kEpiGroups; ++g)      // every epilogue group's next tile index reads "end"
+                        tile_ring[(lt + g) & (kTileRing - 1)] = ((static_cast<uint64_t>(lt + g) + 1ull) << 32) | kTileEnd;
+                }
+            }
+            __syncwarp();
+            if (!have) {
+                // the MMA warp learns about the end through the ring as well, but it is parked on this barrier
+                ptx::mbar_wait(bar_empty(s), ph ^ 1u, p.err, kErrEmpty);
+                if (ptx::elect_one()) ptx::mbar_arrive(bar_full(s));
+                __syncwarp();
+                if (lane == 0) stamp(2);
+                break;
+            }
+            const int t = static_cast<int>(t_cur);
             for (int j0 = 0; j0 < p.n_chunks; j0 += spp) {
                 const int ns = min(spp, p.n_chunks - j0);
                 ptx::mbar_wait(bar_empty(s), ph ^ 1u, p.err, kErrEmpty);
@@ -221,6 +352,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 __syncwarp();
                 if (++s == p.n_stages) { s = 0; ph ^= 1u; }
             }
+            t_cur = dynamic ? __shfl_sync(kFullMask, t_next, 0) : t_next;
         }
     } else if (warp == 1) {
         // =========================== MMA issuer ===========================
@@ -232,10 +364,14 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         const uint32_t slab_lo = static_cast<uint32_t>(p.q_box_rows) * 8u;      // slab bytes >> 4
         ptx::mbar_wait(bar_q, 0, p.err, kErrQFull);
         ptx::tc_fence_after();
+        if (lane == 0) stamp(1);
         const int spp = p.sub_per_stage;
         int s = 0;
         uint32_t ph = 0;
-        for (int lt = 0; lt < my_tiles; ++lt) {
+        for (int lt = 0;; ++lt) {
+            ptx::mbar_wait(bar_full(s), ph, p.err, kErrFull);      // first stage of tile lt, or the end marker
+            if (lt == 1 && lane == 0) stamp(10);
+            if (ring_wait(lt) == kTileEnd) break;
             const int buf = lt & (kBufs - 1);
             const uint32_t bph = (lt / kBufs) & 1u;
             ptx::mbar_wait(bar_tempty(buf), bph ^ 1u, p.err, kErrTmemEmpty);
@@ -243,7 +379,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             const uint32_t d_tmem = tmem_base + kAccCol0 + buf * kTileRows;
             for (int j0 = 0; j0 < p.n_chunks; j0 += spp) {
                 const int ns = min(spp, p.n_chunks - j0);
-                ptx::mbar_wait(bar_full(s), ph, p.err, kErrFull);
+                if (j0 > 0) ptx::mbar_wait(bar_full(s), ph, p.err, kErrFull);
                 ptx::tc_fence_after();
                 if (ptx::elect_one()) {
 #pragma unroll
@@ -276,9 +412,9 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     } else {
         // =========================== epilogue: streaming top-k ===========================
         // The 32 lanes of a warp are 32 independent queries, so everything here is thread-private: a lane keeps its
-        // admission threshold (score of its current kk-th best) in a register, appends the rare scores that beat it
-        // to its own pending buffer in shared memory, and — when some lane's buffer runs full — every lane folds
-        // its own pending candidates into its own sorted list.  No cross-lane traffic except one vote per 8 scores.
+        // admission threshold in a register, appends the rare scores that beat it to its own pending buffer in shared
+        // memory, and — when some lane's buffer runs full — every lane folds its own pending candidates into its own
+        // sorted list.  No cross-lane traffic except one vote per 8 scores.
         const int grp = (warp - 2) >> 2;               // epilogue group: owns tiles grp, grp + 2, ...
         const int quad = warp & 3;                     // TMEM lane quadrant this warp may read
         const int row = quad * 32 + lane;              // query slot (TMEM lane) owned by this thread
@@ -290,36 +426,97 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         uint64_t* my_list = lists + static_cast<size_t>(grp * kUmmaM + row) * scan_row_stride(kk_pad, p.cand_cap);   // [0, kk)
         uint2* my_pend = reinterpret_cast<uint2*>(my_list + kk_pad);                      // (score bits, row)
         const bool active_group = grp < p.n_epi_groups;      // an idle group owns no list memory
-        if (active_group) for (int i = 0; i < kk; ++i) my_list[i] = 0ull;
+        if (!kRegList && active_group) for (int i = 0; i < kk; ++i) my_list[i] = 0ull;
+        // thr = max(private threshold: score of this list's kk-th best, shared threshold: just below the minimum over
+        // the query's ns published slot maxima).  `>` is exact for both: rows arrive in ascending order, so a later row
+        // displaces the kk-th best only with a STRICTLY higher score; and ns distinct rows are known to score at least
+        // the shared value, so only scores >= it (i.e. > its predecessor) can still matter, whatever their row.
+        float thr_own = -CUDART_INF_F, thr_shared = -CUDART_INF_F;
         float thr = valid ? -CUDART_INF_F : CUDART_INF_F;
+        float best = -CUDART_INF_F, best_published = -CUDART_INF_F;
         int n_pend = 0;
         const int flush_at = p.cand_cap - 8;           // the next group of 8 scores must always fit
+        // The list is kept UNSORTED while the scan runs: an admitted candidate overwrites the current minimum and the new
+        // minimum is found by one pass of independent loads (no store chain) — a sorted insert costs a dependent
+        // load/compare/store per shifted element, which for k+s = 16..32 was most of the kernel's time (round 1: 43 % /
+        // 24 % of the HBM roofline).  The list is sorted once, when the CTA writes its partial result.
+        int n_list = 0, min_pos = 0;
+        uint64_t min_key = 0ull;
 
+        auto find_min = [&]() {
+            uint64_t mk = my_list[0];
+            int mp = 0;
+#pragma unroll 8
+            for (int j = 1; j < kk; ++j) {
+                const uint64_t v = my_list[j];
+                if (v < mk) { mk = v; mp = j; }
+            }
+            min_key = mk;
+            min_pos = mp;
+        };
         auto flush = [&]() {
+            if (p.dbg) {
+                atomicAdd(p.dbg + 0, static_cast<unsigned long long>(n_pend));
+                if (lane == 0) atomicAdd(p.dbg + 1, 1ull);
+            }
             for (int c = 0; c < n_pend; ++c) {
                 const uint2 cand = my_pend[c];
                 const uint64_t key = make_key(__uint_as_float(cand.x), cand.y);
-                uint64_t lower = my_list[kk - 1];
-                if (key > lower) {
-                    // Branch-free single pass from the bottom: new[j] = old[j-1] >= key ? max(old[j], key) : old[j-1].
-                    // No iteration depends on a loaded value for control flow, so the LDS/STS stream pipelines
-                    // (a compare-and-break insertion loop pays one shared-memory latency per shifted element).
-#pragma unroll 4
-                    for (int j = kk - 1; j > 0; --j) {
-                        const uint64_t upper = my_list[j - 1];
-                        my_list[j] = upper >= key ? (lower > key ? lower : key) : upper;
-                        lower = upper;
-                    }
-                    my_list[0] = lower > key ? lower : key;
+                if (n_list < kk) {
+                    my_list[n_list++] = key;
+                    if (n_list == kk) find_min();
+                } else if (key > min_key) {
+                    my_list[min_pos] = key;
+                    find_min();
+                    if (p.dbg) atomicAdd(p.dbg + 3, 1ull);
                 }
             }
             n_pend = 0;
-            const uint64_t kth = my_list[kk - 1];
-            if (valid) thr = kth == 0ull ? -CUDART_INF_F : key_score(kth);
+            thr_own = n_list == kk ? key_score(min_key) : -CUDART_INF_F;
+            if (valid) thr = fmaxf(thr_own, thr_shared);
+        };
+        // register list (kRegList): slots >= kk hold ~0 so that they are never the minimum; 0 = empty = smaller than any key
+        uint64_t L[8];
+        uint64_t rmin_key = 0ull;
+        int rmin_pos = 0;
+        if constexpr (kRegList) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) L[j] = j < kk ? 0ull : ~0ull;
+        }
+        auto reg_insert = [&](float score, uint32_t gidx) {      // caller: score > thr  (=> key > rmin_key)
+            const uint64_t key = make_key(score, gidx);
+            uint64_t mk = ~0ull;
+            int mp = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                L[j] = j == rmin_pos ? key : L[j];
+                if (L[j] < mk) { mk = L[j]; mp = j; }
+            }
+            rmin_key = mk;
+            rmin_pos = mp;
+            thr_own = mk == 0ull ? -CUDART_INF_F : key_score(mk);
+            thr = fmaxf(thr_own, thr_shared);                      // only valid lanes ever get here
+            best = fmaxf(best, score);
+        };
+        // descending selection sort of the n_list live entries; the tail [n_list, kk) stays zero (= empty)
+        auto sort_list = [&]() {
+            for (int i = 0; i + 1 < n_list; ++i) {
+                uint64_t mk = my_list[i];
+                int mp = i;
+                for (int j = i + 1; j < n_list; ++j) {
+                    const uint64_t v = my_list[j];
+                    if (v > mk) { mk = v; mp = j; }
+                }
+                if (mp != i) {
+                    my_list[mp] = my_list[i];
+                    my_list[i] = mk;
+                }
+            }
         };
 
-        if (kQTmem && grp == 0) {
-            // This thread's query row -> its TMEM lane, columns [0, D/2): 8 bf16 (one uint4) fill 4 columns.
+        if constexpr (kQTmem) {
+            // This thread's query row -> its TMEM lane, columns [0, D/2): 8 bf16 (one uint4) fill 4 columns.  The two
+            // epilogue groups split the row's 64-element chunks between them (both can reach every lane quadrant).
             const uint32_t q_taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
             const size_t qrow_idx = static_cast<size_t>(valid ? q0 + row : 0);
             if constexpr (kFuseQ) {
@@ -339,7 +536,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                     scale = ss > 0.f ? 1.0f / sqrtf(ss) : 0.f;
                 }
                 float rs = 0.f;
-                for (int c0 = 0; c0 < p.d / 2; c0 += 32) {
+                for (int c0 = grp * 32; c0 < p.d / 2; c0 += 64) {
                     uint32_t w[32];
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
@@ -358,10 +555,14 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                     }
                     ptx::tmem_st_32x32b_x32(q_taddr + c0, w);
                 }
-                if (valid && split == 0 && p.q_bias_out) p.q_bias_out[q0 + row] = -0.5f * rs;
+                if (split == 0 && p.q_bias_out) {                   // -0.5*|q|^2 for return_dists: the two halves meet here
+                    scratch[grp * kUmmaM + row] = rs;
+                    ptx::named_bar_sync(3, 256);
+                    if (grp == 0 && valid) p.q_bias_out[q0 + row] = -0.5f * (rs + scratch[kUmmaM + row]);
+                }
             } else {
                 const uint4* qrow = reinterpret_cast<const uint4*>(p.q + qrow_idx * p.d);
-                for (int c0 = 0; c0 < p.d / 2; c0 += 32) {
+                for (int c0 = grp * 32; c0 < p.d / 2; c0 += 64) {
                     uint32_t w[32];
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
@@ -376,95 +577,191 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(bar_q);
+        } else if constexpr (kFuseQ) {
+            // shared-memory q-tile filled by the eight epilogue warps, a warp per row (coalesced 1 KiB reads)
+            const uint32_t slab_bytes = static_cast<uint32_t>(p.q_box_rows) * 128u;
+            for (int r = warp - 2; r < p.q_box_rows; r += 8) {
+                const bool real = q0 + r < p.b_total;
+                const float rs = prep_query_row_to_smem(p, q0 + r, real, smem + lay.q_off, slab_bytes, r, lane);
+                if (lane == 0 && real && r < q_valid && split == 0 && p.q_bias_out) p.q_bias_out[q0 + r] = -0.5f * rs;
+            }
+            ptx::fence_proxy_async_smem();       // generic-proxy stores -> visible to the tensor core's async proxy
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(bar_q);
         }
 
-        auto load_bias = [&](int t) -> float {
-            const int r = t * kTileRows + ep_tid;
-            return (r < p.n_local) ? __ldg(p.bias + r) : -CUDART_INF_F;   // -inf masks rows past the shard end
+        auto load_bias = [&](uint32_t t) -> float {
+            const uint32_t r = t * kTileRows + ep_tid;
+            return (r < static_cast<uint32_t>(p.n_local)) ? __ldg(p.bias + r) : -CUDART_INF_F;   // -inf masks rows past the shard end
         };
-        // With n_epi_groups == 1 group 1 idles: it only writes its (empty) lists.  Used when list maintenance dominates
-        // and both groups' active warps would share one SM sub-partition anyway (few queries, large k).
+        // shared threshold: minimum over this query's ns slots (0 = some slot still empty -> no bound yet)
+        const int my_slot_ = p.gthr ? (split * kEpiGroups + grp) % p.ns : 0;
+        const uint32_t* my_gthr = p.gthr ? p.gthr + static_cast<size_t>(valid ? q0 + row : 0) * p.ns : nullptr;
+        auto refresh_shared = [&]() {
+            uint32_t m = 0xFFFFFFFFu;
+            for (int i = 0; i < p.ns; i += 4) {
+                const uint4 v = __ldcg(reinterpret_cast<const uint4*>(my_gthr + i));
+                m = min(min(m, v.x), min(min(v.y, v.z), v.w));
+            }
+            // strictly-below-m in the ordered domain: scores >= m stay admissible (their row may still win a tie)
+            if (m > 0x00800000u) {
+                thr_shared = fmaxf(thr_shared, __uint_as_float(ordered_to_f32(m - 1u)));
+                if (valid) thr = fmaxf(thr_own, thr_shared);
+                if (p.dbg && valid) atomicAdd(p.dbg + 5, 1ull);
+            }
+        };
+        // publish this list's best score: the minimum over a query's slots bounds its global kk-th best from below
+        auto publish_best = [&]() {
+            if (valid && best > best_published) {
+                atomicMax(p.gthr + static_cast<size_t>(q0 + row) * p.ns + my_slot_, f32_to_ordered(__float_as_uint(best)));
+                best_published = best;
+            }
+        };
+        // With n_epi_groups == 1 group 1 idles in the main loop: it only helped to load the q-tile.
         const int n_groups = p.n_epi_groups;
-        const int first_tile = grp < n_groups ? grp : my_tiles;
-        float next_bias = first_tile < my_tiles ? load_bias(tile_begin + first_tile) : 0.f;
+        bool have_bias = false;
+        float next_bias = 0.f;
+        int done_tiles = 0, next_refresh = 1;
 
-        for (int lt = first_tile; lt < my_tiles; lt += n_groups) {
-            const int t = tile_begin + lt;
-            const int buf = lt & (kBufs - 1);
-            const uint32_t bph = (lt / kBufs) & 1u;
-            // bias tiles are double-buffered per group: a fast warp may stage tile lt+2 while a slow one still reads lt
-            float* bias_tile = bias_s + (grp * 2 + ((lt / n_groups) & 1)) * kTileRows;
-            bias_tile[ep_tid] = next_bias;
-            ptx::named_bar_sync(1 + grp, 128);
-            if (lt + n_groups < my_tiles) next_bias = load_bias(t + n_groups);
+        if (active_group) {
+            for (int lt = grp;; lt += n_groups) {
+                const uint32_t t = ring_wait(lt);
+                if (t == kTileEnd) break;
+                const int buf = lt & (kBufs - 1);
+                const uint32_t bph = (lt / kBufs) & 1u;
+                if (!have_bias) next_bias = load_bias(t);
+                // bias tiles are double-buffered per group: a fast warp may stage tile lt+2 while a slow one still reads lt
+                float* bias_tile = bias_s + (grp * 2 + ((lt / n_groups) & 1)) * kTileRows;
+                bias_tile[ep_tid] = next_bias;
+                ptx::named_bar_sync(1 + grp, 128);
+                {   // the producer is normally a tile or two ahead: fetch the next tile's bias under this tile's work
+                    const uint64_t e = tile_ring[(lt + n_groups) & (kTileRing - 1)];
+                    have_bias = (e >> 32) == static_cast<uint64_t>(lt + n_groups) + 1ull && static_cast<uint32_t>(e) != kTileEnd;
+                    if (have_bias) next_bias = load_bias(static_cast<uint32_t>(e));
+                }
+                if (my_gthr && done_tiles >= next_refresh) {
+                    refresh_shared();
+                    next_refresh = done_tiles + max(1, done_tiles >> 1);
+                }
 
-            ptx::mbar_wait(bar_tfull(buf), bph, p.err, kErrTmemFull);
-            ptx::tc_fence_after();
+                ptx::mbar_wait(bar_tfull(buf), bph, p.err, kErrTmemFull);
+                ptx::tc_fence_after();
+                if (done_tiles == 0 && grp == 0 && lane == 0 && quad == 0) stamp(15);
 
-            if (warp_has_work) {
-                const uint32_t row_base = static_cast<uint32_t>(t) * kTileRows;
+                if (warp_has_work) {
+                    const uint32_t row_base = t * kTileRows;
 #pragma unroll 1
-                for (int c0 = 0; c0 < kTileRows; c0 += 32) {
-                    uint32_t v[32];
-                    ptx::tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + kAccCol0 +
-                                                buf * kTileRows + c0, v);
-                    ptx::tmem_wait_ld();
+                    for (int c0 = 0; c0 < kTileRows; c0 += 32) {
+                        uint32_t v[32];
+                        ptx::tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + kAccCol0 +
+                                                    buf * kTileRows + c0, v);
+                        ptx::tmem_wait_ld();
+                        if (done_tiles == 0 && my_gthr) {
+                            // first tile: make this chunk's best score public BEFORE working on it (any real row's score
+                            // is a valid contribution to a slot), so that the other lists' refreshes find it
+                            float cm = -CUDART_INF_F;
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        float s[8];
-                        const float4 b0 = *reinterpret_cast<const float4*>(bias_tile + c0 + g * 8);
-                        const float4 b1 = *reinterpret_cast<const float4*>(bias_tile + c0 + g * 8 + 4);
-                        s[0] = __uint_as_float(v[g * 8 + 0]) + b0.x;
-                        s[1] = __uint_as_float(v[g * 8 + 1]) + b0.y;
-                        s[2] = __uint_as_float(v[g * 8 + 2]) + b0.z;
-                        s[3] = __uint_as_float(v[g * 8 + 3]) + b0.w;
-                        s[4] = __uint_as_float(v[g * 8 + 4]) + b1.x;
-                        s[5] = __uint_as_float(v[g * 8 + 5]) + b1.y;
-                        s[6] = __uint_as_float(v[g * 8 + 6]) + b1.z;
-                        s[7] = __uint_as_float(v[g * 8 + 7]) + b1.w;
-                        if constexpr (kDump) {
-                            if (valid) {
+                            for (int i = 0; i < 32; ++i) cm = fmaxf(cm, __uint_as_float(v[i]) + bias_tile[c0 + i]);
+                            best = fmaxf(best, cm);
+                            publish_best();
+                        }
 #pragma unroll
-                                for (int i = 0; i < 8; ++i) {
-                                    const uint32_t r = row_base + c0 + g * 8 + i;
-                                    if (r < static_cast<uint32_t>(p.n_local))
-                                        p.dump[static_cast<size_t>(q0 + row) * p.n_local + r] = s[i];
+                        for (int g = 0; g < 4; ++g) {
+                            float s[8];
+                            const float4 b0 = *reinterpret_cast<const float4*>(bias_tile + c0 + g * 8);
+                            const float4 b1 = *reinterpret_cast<const float4*>(bias_tile + c0 + g * 8 + 4);
+                            s[0] = __uint_as_float(v[g * 8 + 0]) + b0.x;
+                            s[1] = __uint_as_float(v[g * 8 + 1]) + b0.y;
+                            s[2] = __uint_as_float(v[g * 8 + 2]) + b0.z;
+                            s[3] = __uint_as_float(v[g * 8 + 3]) + b0.w;
+                            s[4] = __uint_as_float(v[g * 8 + 4]) + b1.x;
+                            s[5] = __uint_as_float(v[g * 8 + 5]) + b1.y;
+                            s[6] = __uint_as_float(v[g * 8 + 6]) + b1.z;
+                            s[7] = __uint_as_float(v[g * 8 + 7]) + b1.w;
+                            if constexpr (kDump) {
+                                if (valid) {
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) {
+                                        const uint32_t r = row_base + c0 + g * 8 + i;
+                                        if (r < static_cast<uint32_t>(p.n_local))
+                                            p.dump[static_cast<size_t>(q0 + row) * p.n_local + r] = s[i];
+                                    }
+                                }
+                            }
+                            const float m = fmaxf(fmaxf(fmaxf(s[0], s[1]), fmaxf(s[2], s[3])),
+                                                  fmaxf(fmaxf(s[4], s[5]), fmaxf(s[6], s[7])));
+                            if (__any_sync(kFullMask, m > thr)) {
+                                if (p.dbg && lane == 0) atomicAdd(p.dbg + 2, 1ull);
+                                const uint32_t gidx = p.idx_base + row_base + c0 + g * 8;
+                                if constexpr (kRegList) {
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i)
+                                        if (s[i] > thr) reg_insert(s[i], gidx + i);
+                                } else {
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) {
+                                        if (s[i] > thr) {
+                                            my_pend[n_pend] = make_uint2(__float_as_uint(s[i]), gidx + i);
+                                            ++n_pend;
+                                        }
+                                    }
+                                    if (m > thr) best = fmaxf(best, m);
+                                    if (__any_sync(kFullMask, n_pend > flush_at)) flush();
                                 }
                             }
                         }
-                        const float m = fmaxf(fmaxf(fmaxf(s[0], s[1]), fmaxf(s[2], s[3])),
-                                              fmaxf(fmaxf(s[4], s[5]), fmaxf(s[6], s[7])));
-                        if (__any_sync(kFullMask, m > thr)) {
-                            // Rows arrive in ascending order, so a later row can only displace the kk-th best with a
-                            // STRICTLY higher score: `>` is the exact admission test for (score desc, row asc).
-                            const uint32_t gidx = p.idx_base + row_base + c0 + g * 8;
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                if (s[i] > thr) {
-                                    my_pend[n_pend] = make_uint2(__float_as_uint(s[i]), gidx + i);
-                                    ++n_pend;
-                                }
-                            }
-                            if (__any_sync(kFullMask, n_pend > flush_at)) flush();
-                        }
+                        // First tile of this list: nothing is known about the query yet and every CTA starts blind at the
+                        // same moment.  Publishing every 32 rows and refreshing before the next 32 lets the ~300 lists
+                        // bootstrap one another within the first tile instead of each paying for a full blind tile.
+                        if (done_tiles == 0 && my_gthr) refresh_shared();
                     }
                 }
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(bar_tempty(buf));
+                if (my_gthr) publish_best();
+                ++done_tiles;
+                if (p.dbg && lane == 0 && warp_has_work) atomicAdd(p.dbg + 4, 1ull);
+                if (done_tiles == 1 && lane == 0 && quad == 0) stamp(11 + grp);
+                if (done_tiles == 4 && lane == 0 && quad == 0) stamp(13 + grp);
             }
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(bar_tempty(buf));
         }
 
+        if (lane == 0 && quad == 0) stamp(3 + 2 * grp);
         // partial result of this (split, group, q-tile): part_keys[q0 + row][rank][split * 2 + grp] — rank-major per
-        // query, so the merge kernel's walk over all lists' rank-i candidates is one contiguous stream
+        // query, so the merge's walk over all lists' rank-i candidates is one contiguous stream
         if (warp_has_work) {
-            if (active_group) flush();
-            if (valid) {
-                const size_t n_lists = static_cast<size_t>(p.n_splits) * kEpiGroups;
-                uint64_t* dst = p.part_keys + static_cast<size_t>(q0 + row) * kk * n_lists + split * kEpiGroups + grp;
-                for (int i = 0; i < kk; ++i) dst[static_cast<size_t>(i) * n_lists] = active_group ? my_list[i] : 0ull;
+            const size_t n_lists = static_cast<size_t>(p.n_splits) * kEpiGroups;
+            uint64_t* dst = p.part_keys + static_cast<size_t>(q0 + row) * kk * n_lists + split * kEpiGroups + grp;
+            if constexpr (kRegList) {
+                // descending sort of the 8 registers (odd-even transposition network), unused slots sink to the end
+#pragma unroll
+                for (int j = 0; j < 8; ++j) L[j] = (j < kk && active_group) ? L[j] : 0ull;
+#pragma unroll
+                for (int round = 0; round < 8; ++round) {
+#pragma unroll
+                    for (int j = round & 1; j + 1 < 8; j += 2) {
+                        const uint64_t hi = L[j] > L[j + 1] ? L[j] : L[j + 1];
+                        const uint64_t lo = L[j] > L[j + 1] ? L[j + 1] : L[j];
+                        L[j] = hi;
+                        L[j + 1] = lo;
+                    }
+                }
+                if (valid) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        if (i < kk) dst[static_cast<size_t>(i) * n_lists] = L[i];
+                }
+            } else {
+                if (active_group) {
+                    flush();
+                    sort_list();
+                }
+                if (valid)
+                    for (int i = 0; i < kk; ++i) dst[static_cast<size_t>(i) * n_lists] = active_group ? my_list[i] : 0ull;
             }
         }
+        if (lane == 0 && quad == 0) stamp(4 + 2 * grp);
     }
 
     // ---- teardown
@@ -472,9 +769,41 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     ptx::tc_fence_before();
     __syncthreads();
     if constexpr (kCluster > 1) ptx::cluster_sync();      // no CTA leaves while a peer may still signal its barriers
+    if (threadIdx.x == 0) stamp(7);
     if (warp == 1) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc(tmem_base, kTmemCols);
+    }
+
+    // ---- fused tail: once every CTA's partial lists are in memory, warps finish whole queries (merge -> [exchange] ->
+    //      vote -> prompt ids); the last CTA out re-zeroes the control block.  Requires a co-resident grid.
+    if constexpr (!kDump && kCluster == 1) {
+        if (p.fused_tail) {
+            if (threadIdx.x == 0) {
+                __threadfence();
+                atomicAdd(tail.ctrl, 1u);
+                if (ld_acquire_gpu_u32(tail.ctrl) < gridDim.x) {
+                    const uint64_t t0 = ptx::globaltimer_ns();
+                    uint32_t polls = 0;
+                    while (ld_acquire_gpu_u32(tail.ctrl) < gridDim.x) {
+                        if ((++polls & 0x3FFu) == 0 && ptx::globaltimer_ns() - t0 > 8000000000ull) {
+                            if (p.err) atomicCAS(p.err, 0, kErrGridBarrier);
+                            __threadfence_system();
+                            __trap();
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) stamp(8);
+            uint32_t e = 0;
+            if (tail.xchg.world > 1) e = *reinterpret_cast<volatile uint32_t*>(tail.xchg.peers.buf[tail.xchg.rank]) + 1u;
+            for (int q = blockIdx.x + gridDim.x * warp; q < tail.b; q += gridDim.x * kScanWarps)
+                warp_tail_query(tail, q, e, lane);
+            __syncthreads();
+            if (threadIdx.x == 0) stamp(9);
+            if (threadIdx.x == 0) tail_ticket(tail, e, gridDim.x);
+        }
     }
 }
 

@@ -1,0 +1,344 @@
+// The tail of a retrieval step — everything that follows the bank scan for ONE query, written as warp-level device
+// functions so that it can run (a) inside the scan kernel itself after its grid barrier (one launch per step) and
+// (b) as the stand-alone kernels of the multi-launch path (merge_topk.cuh, prompt_gather.cuh, tail_kernel below):
+//
+//   1. k-way merge of the per-(split, epilogue group) partial lists the scan left in its workspace
+//   2. multi-GPU only: push the local top-kk into every peer's exchange buffer over NVLink (plain P2P stores + a
+//      release flag per query), wait for every rank's delivery of the same query, merge the `world` lists
+//   3. answers of the retrieved rows -> majority vote -> quantifier bucket -> prompt token ids
+//
+// Replaces the second half of torch.argsort(...)[:, s:s+k] (/root/reference/dataset/VQAFeatureDataset.py:195,197), the
+// answer gather / vote / quantifier sentence (:199,215-230) and the tokenizer call of
+// /root/reference/architectures/T5VisionModel.py:153-167.  The cross-GPU exchange is new (the reference is
+// single-device, /root/reference/main.py:58-61).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <math_constants.h>
+
+#include "ptx.cuh"
+#include "topk_key.cuh"
+
+namespace mpr {
+
+// ------------------------------------------------------------------------------------------------ k-way merge
+// Candidate (list l, rank i) lives at base[l*stride_l + i*stride_i]; every list is sorted descending over i, 0 = empty.
+// The walk is rank-major (all lists' best, then all second-best, ...).  Because every list is sorted, a rank at which no
+// list contributes ends the merge: no later rank can beat the threshold either.  Returns the merged list, one element per
+// lane (lanes >= kk are scratch).  kCoherent: bypass L1 (the lists were written by other SMs / GPUs during this launch).
+constexpr int kMergeUnroll = 8;
+
+template <bool kCoherent>
+__device__ __forceinline__ uint64_t load_key(const uint64_t* p) {
+    if constexpr (kCoherent) return __ldcg(reinterpret_cast<const unsigned long long*>(p));
+    else return *p;
+}
+
+template <bool kCoherent>
+__device__ __forceinline__ uint64_t warp_merge_lists(const uint64_t* __restrict__ base, int n_lists, long long stride_l,
+                                                     long long stride_i, int kk, int lane) {
+    uint64_t elem = 0ull;        // lane i holds element i of the running list
+    uint64_t kth = 0ull;         // admission threshold: max(element kk-1, floor)
+    uint64_t floor = 0ull;       // a key known to be below the final kk-th best (0 = none)
+    for (int i = 0; i < kk; ++i) {
+        bool admitted = false;
+        const uint64_t* rank_base = base + static_cast<long long>(i) * stride_i;
+        for (int l0 = 0; l0 < n_lists; l0 += 32 * kMergeUnroll) {
+            uint64_t key[kMergeUnroll];
+#pragma unroll
+            for (int u = 0; u < kMergeUnroll; ++u) {          // all loads of the chunk in flight before any use
+                const int l = l0 + u * 32 + lane;
+                key[u] = l < n_lists ? load_key<kCoherent>(rank_base + static_cast<long long>(l) * stride_l) : 0ull;
+            }
+            if (i == 0 && l0 == 0 && n_lists >= 64) {
+                // Pivot: the kk-th largest of the 32 lanes' local maxima is a key that at least kk candidates reach, so
+                // everything below it can skip the serial insert loop (with ~300 lists that is all but ~2*kk of them).
+                uint64_t lm = key[0];
+#pragma unroll
+                for (int u = 1; u < kMergeUnroll; ++u) lm = key[u] > lm ? key[u] : lm;
+                int rank = 0;
+                for (int o = 1; o < 32; ++o) rank += shfl_u64(lm, (lane + o) & 31) > lm ? 1 : 0;
+                const unsigned who = __ballot_sync(kFullMask, rank == kk - 1 && lm != 0ull);
+                if (who) {
+                    floor = shfl_u64(lm, __ffs(who) - 1) - 1ull;
+                    kth = floor;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kMergeUnroll; ++u) {
+                if (l0 + u * 32 >= n_lists) break;
+                unsigned pending = __ballot_sync(kFullMask, key[u] > kth);
+                while (pending) {
+                    const int src = __ffs(pending) - 1;
+                    pending &= pending - 1;
+                    const uint64_t cand = shfl_u64(key[u], src);
+                    if (cand > kth) {    // uniform: the threshold may have moved since the ballot
+                        elem = warp_list_insert(elem, cand, lane);
+                        const uint64_t last = shfl_u64(elem, kk - 1);
+                        kth = last > floor ? last : floor;
+                        admitted = true;
+                    }
+                }
+            }
+        }
+        if (!admitted) break;
+    }
+    return elem;
+}
+
+__device__ __forceinline__ void store_merged(uint64_t elem, int q, int kk, int lane, uint64_t* out_keys, float* out_score,
+                                             int32_t* out_idx) {
+    if (lane < kk) {
+        const size_t o = static_cast<size_t>(q) * kk + lane;
+        if (out_keys) out_keys[o] = elem;
+        if (out_score) out_score[o] = elem == 0ull ? -CUDART_INF_F : key_score(elem);
+        if (out_idx) out_idx[o] = key_row(elem);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ peer-memory exchange
+// Every rank owns one exchange buffer of identical layout, mapped into every peer (symmetric memory), zero-filled once:
+//
+//   byte 0      u32 epoch                 last exchange this rank has fully consumed
+//   byte 4      u32 done                  tail tickets of the launch in flight (stand-alone tail kernel only)
+//   byte 1024   u32 flag[world][cap]      flag[r][q] = newest epoch whose query-q candidates rank r delivered INTO THIS buffer
+//   then        u64 slot[2][world][cap]   candidate lists ([q][kk] inside a slot), double-buffered on epoch parity
+//
+// Exchange e = epoch + 1.  For query q a warp stores its kk keys into slot[e&1][my_rank] of EVERY rank's buffer,
+// fences (fence.sys) and releases flag[my_rank][q] = e on every rank; then it waits (ld.acquire.sys) until its own
+// buffer shows flag[r][q] >= e for all r and merges slot[e&1][0..world) in rank order (= global row order, so ties still
+// resolve to the lower row).  The last warp of the launch publishes epoch = e.
+// Why two slots are enough: a rank can start exchange e+1 (writing slot[(e+1)&1]) while a slow peer still reads
+// slot[e&1], but it cannot reach e+2 before that peer has delivered its own e+1 flags, which it does only after its
+// merge of e.  The waiting warp only ever waits on OTHER GPUs, never on a kernel that must be co-scheduled on its own.
+// Sharded search is therefore a COLLECTIVE call: every rank must issue the same sequence of searches.
+constexpr int kXchgMaxWorld = 16;
+constexpr int kXchgFlagOff = 1024;
+constexpr int kErrXchgTimeout = 201;
+
+struct XchgPeers {
+    unsigned char* buf[kXchgMaxWorld];
+};
+
+struct XchgParams {
+    int world, rank, cap;          // world <= 1: no exchange
+    unsigned long long timeout_ns; // how long a warp waits for a peer before it gives up (status = kErrXchgTimeout)
+    XchgPeers peers;               // peers.buf[rank] = this rank's own buffer
+};
+
+__host__ __device__ inline size_t xchg_slot_off(int world, int cap) {
+    return (static_cast<size_t>(kXchgFlagOff) + static_cast<size_t>(world) * cap * sizeof(uint32_t) + 15u) & ~size_t(15);
+}
+__host__ __device__ inline size_t xchg_bytes(int world, int cap) {
+    return xchg_slot_off(world, cap) + 2ull * world * cap * sizeof(uint64_t);
+}
+
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Exchange of one query's merged local list (`elem`, one element per lane) with all ranks; returns the global list.
+// `e` is the exchange epoch of this launch.  On a timeout *status receives kErrXchgTimeout and the LOCAL list is returned.
+__device__ __forceinline__ uint64_t warp_exchange(const XchgParams& x, uint32_t e, uint64_t elem, int q, int kk, int lane,
+                                                  int* status) {
+    const size_t slot_off = xchg_slot_off(x.world, x.cap);
+    const size_t slot = (static_cast<size_t>(e & 1u) * x.world + x.rank) * x.cap + static_cast<size_t>(q) * kk;
+    if (lane < kk) {
+        for (int r = 0; r < x.world; ++r)
+            reinterpret_cast<uint64_t*>(x.peers.buf[r] + slot_off)[slot + lane] = elem;
+    }
+    __threadfence_system();
+    __syncwarp();
+    if (lane < x.world)
+        st_release_sys_u32(reinterpret_cast<uint32_t*>(x.peers.buf[lane] + kXchgFlagOff) +
+                               static_cast<size_t>(x.rank) * x.cap + q, e);
+    unsigned char* mine = x.peers.buf[x.rank];
+    bool ok = true;
+    if (lane < x.world) {
+        const uint32_t* flag = reinterpret_cast<const uint32_t*>(mine + kXchgFlagOff) + static_cast<size_t>(lane) * x.cap + q;
+        if (static_cast<int32_t>(ld_acquire_sys_u32(flag) - e) < 0) {
+            const uint64_t t0 = ptx::globaltimer_ns();
+            uint32_t polls = 0;
+            while (static_cast<int32_t>(ld_acquire_sys_u32(flag) - e) < 0) {
+                if ((++polls & 0xFFu) == 0 && ptx::globaltimer_ns() - t0 > x.timeout_ns) {
+                    ok = false;
+                    break;
+                }
+            }
+        }
+    }
+    if (!__all_sync(kFullMask, ok)) {
+        if (lane == 0 && status) atomicMax(status, kErrXchgTimeout);
+        return elem;
+    }
+    const uint64_t* slots = reinterpret_cast<const uint64_t*>(mine + slot_off) +
+                            static_cast<size_t>(e & 1u) * x.world * x.cap + static_cast<size_t>(q) * kk;
+    return warp_merge_lists<true>(slots, x.world, x.cap, 1ll, kk, lane);
+}
+
+// ------------------------------------------------------------------------------------------------ vote + prompt ids
+// Tokenisation is done by concatenating pre-tokenised segments (sentencepiece never merges across whitespace):
+//   prefix_q  = tokens("Answer the {task} question: " + question + "I" | "The")      host, per query
+//   seg 0 / 1 = tokens("believe the answer is") / tokens("most frequent answer is")
+//   seg 2..7  = tokens(bucket b),   seg 8+a = tokens(answer a)                        host, once per bank
+constexpr int kSegQuant = 0, kSegPlain = 1, kSegBucket0 = 2, kSegAnswer0 = 8;
+
+struct PromptParams {
+    const int32_t* idx;         // [b][kk] global bank rows, -1 = none (stand-alone kernel only)
+    int b, kk, skip;            // k = kk - skip votes per query, taken from ranks skip..kk-1
+    const int32_t* answer_id;   // [n_total] interned answer of every bank row; nullptr = no prompt stage
+    const uint8_t* bucket_lut;  // [(k+1)*(k+1)]: lut[n_votes*(k+1) + max_count] = int(max_count/n_votes*5)
+    const int32_t* prefix_ids;  // CSR over queries
+    const int32_t* prefix_off;  // [b+1]
+    const int32_t* seg_ids;     // CSR over segments
+    const int32_t* seg_off;     // [8 + n_answers + 1]
+    int use_quantifier;
+    int pad_id, eos_id;
+    int max_len;                // tokenizer max_length (truncation), eos included
+    int out_stride;             // row pitch of input_ids / attention_mask
+    long long* input_ids;       // [b][out_stride]
+    long long* attention_mask;  // [b][out_stride]
+    int32_t* out_len;           // [b] tokens incl. eos
+    int32_t* maj_answer;        // [b] answer id of the vote winner (-1 if no votes)
+    int32_t* maj_count;         // [b]
+    int32_t* bucket;            // [b] 0..5
+    int32_t* ret_answer;        // [b][k] answer ids in rank order (or nullptr)
+};
+
+// `row` = bank row retrieved at rank skip + lane (lanes >= k: ignored), -1 = none.
+__device__ __forceinline__ void warp_vote_and_gather(const PromptParams& p, int q, int row, int lane) {
+    const int k = p.kk - p.skip;
+    // ---- gather the answers of the retrieved rows   (VQAFeatureDataset.py:199)
+    int a = -1;
+    if (lane < k) {
+        if (row >= 0) a = __ldg(p.answer_id + row);
+        if (p.ret_answer) p.ret_answer[q * k + lane] = a;
+    }
+    const unsigned voters = __ballot_sync(kFullMask, a >= 0);
+    const int n_votes = __popc(voters);
+
+    // ---- majority vote, ties to the earliest first occurrence   (:216-222)
+    const unsigned same = __match_any_sync(kFullMask, a) & voters;
+    int rank_key = -1;
+    if (a >= 0) rank_key = __popc(same) * 64 + (63 - (__ffs(same) - 1));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rank_key = max(rank_key, __shfl_xor_sync(kFullMask, rank_key, o));
+    int maj = -1, cnt = 0, bkt = 0;
+    if (rank_key >= 0) {
+        cnt = rank_key >> 6;
+        const int first = 63 - (rank_key & 63);
+        maj = __shfl_sync(kFullMask, a, first);
+        bkt = p.bucket_lut[n_votes * (k + 1) + cnt];      // :223-226
+    }
+    if (lane == 0) {
+        p.maj_answer[q] = maj;
+        p.maj_count[q] = cnt;
+        p.bucket[q] = bkt;
+    }
+
+    // ---- token assembly: prefix | const | [bucket] | answer | </s> | pad...   (:228,230; T5VisionModel.py:153-167)
+    const int pre0 = p.prefix_off[q], len_pre = p.prefix_off[q + 1] - pre0;
+    const int seg_c = p.use_quantifier ? kSegQuant : kSegPlain;
+    const int c0 = p.seg_off[seg_c], len_c = p.seg_off[seg_c + 1] - c0;
+    int b0 = 0, len_b = 0;
+    if (p.use_quantifier) { b0 = p.seg_off[kSegBucket0 + bkt]; len_b = p.seg_off[kSegBucket0 + bkt + 1] - b0; }
+    int a0 = 0, len_a = 0;
+    if (maj >= 0) { a0 = p.seg_off[kSegAnswer0 + maj]; len_a = p.seg_off[kSegAnswer0 + maj + 1] - a0; }
+    const int body = min(len_pre + len_c + len_b + len_a, p.max_len - 1);   // HF truncation keeps room for </s>
+    if (lane == 0) p.out_len[q] = body + 1;
+
+    long long* ids = p.input_ids + static_cast<size_t>(q) * p.out_stride;
+    long long* msk = p.attention_mask + static_cast<size_t>(q) * p.out_stride;
+    for (int pos = lane; pos < p.out_stride; pos += 32) {
+        int tok = p.pad_id;
+        if (pos < body) {
+            int o = pos;
+            if (o < len_pre) tok = p.prefix_ids[pre0 + o];
+            else if ((o -= len_pre) < len_c) tok = p.seg_ids[c0 + o];
+            else if ((o -= len_c) < len_b) tok = p.seg_ids[b0 + o];
+            else tok = p.seg_ids[a0 + (o - len_b)];
+        } else if (pos == body) {
+            tok = p.eos_id;
+        }
+        ids[pos] = tok;
+        msk[pos] = pos <= body ? 1 : 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ one query's tail
+// Scan workspace control block (first bytes of the caller's workspace; all-zero before the first launch, and every
+// launch leaves it all-zero again):
+//   u32 arrived     grid barrier of the fused tail / nothing in the multi-launch path
+//   u32 done        tail completion tickets
+//   u32 tile_ctr[n_qtiles]   dynamic tile scheduler, one counter per q-tile
+//   u32 gthr[b][ns]          shared admission thresholds (see scan_topk.cuh)
+struct TailParams {
+    int b, kk;
+    const uint64_t* part_keys;   // [b][kk][n_lists]
+    int n_lists;
+    uint32_t* ctrl;              // -> arrived, done
+    uint32_t* tile_ctr;
+    int n_tile_ctr;
+    uint32_t* gthr;              // [b][ns]
+    int ns;
+    uint64_t* out_keys;          // [b][kk] (each may be nullptr)
+    float* out_score;
+    int32_t* out_idx;
+    int* status;                 // device word: 0 = ok (may be nullptr)
+    XchgParams xchg;
+    PromptParams prompt;
+};
+
+// Runs the whole tail for query q on one warp.  `e` = exchange epoch of this launch (ignored when world <= 1).
+__device__ __forceinline__ void warp_tail_query(const TailParams& t, int q, uint32_t e, int lane) {
+    const size_t n_lists = static_cast<size_t>(t.n_lists);
+    uint64_t elem = warp_merge_lists<true>(t.part_keys + static_cast<size_t>(q) * t.kk * n_lists, t.n_lists, 1ll,
+                                           static_cast<long long>(n_lists), t.kk, lane);
+    if (t.gthr && lane < t.ns) t.gthr[static_cast<size_t>(q) * t.ns + lane] = 0u;     // leave the thresholds zeroed
+    if (t.xchg.world > 1) elem = warp_exchange(t.xchg, e, elem, q, t.kk, lane, t.status);
+    store_merged(elem, q, t.kk, lane, t.out_keys, t.out_score, t.out_idx);
+    if (t.prompt.answer_id) {
+        const uint64_t src = shfl_u64(elem, min(lane + t.prompt.skip, 31));
+        const int row = (lane < t.kk - t.prompt.skip) ? key_row(src) : -1;
+        warp_vote_and_gather(t.prompt, q, row, lane);
+    }
+}
+
+// Completion ticket: the last warp group to finish re-zeroes the control block and publishes the exchange epoch.
+// Call with exactly `n_tickets` callers per launch (one thread each).
+__device__ __forceinline__ void tail_ticket(const TailParams& t, uint32_t e, uint32_t n_tickets) {
+    __threadfence();
+    const uint32_t done = atomicAdd(t.ctrl + 1, 1u);
+    if (done == n_tickets - 1u) {
+        for (int i = 0; i < t.n_tile_ctr; ++i) t.tile_ctr[i] = 0u;
+        t.ctrl[0] = 0u;
+        t.ctrl[1] = 0u;
+        if (t.xchg.world > 1) {
+            __threadfence();
+            *reinterpret_cast<volatile uint32_t*>(t.xchg.peers.buf[t.xchg.rank]) = e;
+        }
+    }
+}
+
+// Stand-alone tail (multi-launch path: grids larger than one wave cannot hold a grid barrier): one warp per query.
+__global__ void __launch_bounds__(128) tail_kernel(const TailParams t) {
+    const int lane = threadIdx.x & 31;
+    const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    uint32_t e = 0;
+    if (t.xchg.world > 1) e = *reinterpret_cast<volatile uint32_t*>(t.xchg.peers.buf[t.xchg.rank]) + 1u;
+    if (q < t.b) warp_tail_query(t, q, e, lane);
+    __syncthreads();
+    if (threadIdx.x == 0) tail_ticket(t, e, gridDim.x);
+}
+
+}  // namespace mpr

@@ -30,8 +30,10 @@ def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
     return C.c_void_p(0 if t is None else t.data_ptr())
 
 
-def _stream() -> C.c_void_p:
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(device=None) -> C.c_void_p:
+    """The caller's current stream ON THE TENSORS' DEVICE (not on whatever device happens to be current); the library
+    itself switches to its handle's device for the launch."""
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 _DTYPES = {torch.float32: _native.SRC_F32, torch.float16: _native.SRC_F16, torch.bfloat16: _native.SRC_BF16}
@@ -54,7 +56,7 @@ def bank_build(src0: torch.Tensor, src1: Optional[torch.Tensor] = None, normalis
         bias = torch.empty((n,), dtype=torch.float32, device=src0.device)
     assert out.is_contiguous() and out.dtype == torch.bfloat16 and tuple(out.shape) == (n, d0 + d1)
     rc = h.lib.mpr_bank_build(h.ptr, _ptr(src0), d0, _ptr(src1), d1, _DTYPES[src0.dtype], n, int(bool(normalise)),
-                              _ptr(out), _ptr(bias), _stream())
+                              _ptr(out), _ptr(bias), _stream(src0.device))
     h.check(rc, "mpr_bank_build")
     return out, bias
 
@@ -99,7 +101,7 @@ def search_topk(q: torch.Tensor, bank: torch.Tensor, bias: torch.Tensor, kk: int
         workspace = torch.empty((max(need, 16),), dtype=torch.uint8, device=dev)
     rc = h.lib.mpr_search_topk(h.ptr, _ptr(q), b, _ptr(bank), _ptr(bias), n_local, idx_base, d, kk, _ptr(out_keys),
                                _ptr(out_score), _ptr(out_idx), _ptr(workspace),
-                               workspace.numel() * workspace.element_size(), _stream())
+                               workspace.numel() * workspace.element_size(), _stream(dev))
     h.check(rc, "mpr_search_topk")
     return out_keys, out_score, out_idx
 
@@ -135,7 +137,7 @@ def search_topk_fused(src0: torch.Tensor, src1: Optional[torch.Tensor], bank: to
     rc = h.lib.mpr_search_topk_fused(h.ptr, _ptr(src0), d0, _ptr(src1), d1, _DTYPES[src0.dtype], int(bool(normalise)), b,
                                      _ptr(bank), _ptr(bias), n_local, idx_base, kk, _ptr(out_keys), _ptr(out_score),
                                      _ptr(out_idx), _ptr(q_bias), _ptr(workspace),
-                                     workspace.numel() * workspace.element_size(), _stream())
+                                     workspace.numel() * workspace.element_size(), _stream(dev))
     h.check(rc, "mpr_search_topk_fused")
     return out_keys, out_score, out_idx, q_bias
 
@@ -154,7 +156,7 @@ def merge_topk(keys: torch.Tensor, out_keys: Optional[torch.Tensor] = None, out_
     if out_idx is None:
         out_idx = torch.empty((b, kk), dtype=torch.int32, device=dev)
     rc = h.lib.mpr_merge_topk(h.ptr, _ptr(keys), n_lists, b, kk, _ptr(out_keys), _ptr(out_score), _ptr(out_idx),
-                              _stream())
+                              _stream(dev))
     h.check(rc, "mpr_merge_topk")
     return out_keys, out_score, out_idx
 
@@ -185,7 +187,7 @@ def prompt_gather(idx: torch.Tensor, skip: int, answer_id: torch.Tensor, bucket_
         h.ptr, _ptr(idx), b, kk, skip, _ptr(answer_id), _ptr(bucket_lut), _ptr(prefix_ids), _ptr(prefix_off),
         _ptr(seg_ids), _ptr(seg_off), int(bool(use_quantifier)), pad_id, eos_id, max_len, out_stride,
         _ptr(out["input_ids"]), _ptr(out["attention_mask"]), _ptr(out["length"]), _ptr(out["majority_answer"]),
-        _ptr(out["majority_count"]), _ptr(out["bucket"]), _ptr(out["answer_ids"]), _stream())
+        _ptr(out["majority_count"]), _ptr(out["bucket"]), _ptr(out["answer_ids"]), _stream(dev))
     h.check(rc, "mpr_prompt_gather")
     return out
 
@@ -199,7 +201,7 @@ def debug_scores(q: torch.Tensor, bank: torch.Tensor, bias: torch.Tensor) -> tor
     need = max(16, search_workspace_bytes(b, n_local, d, 1, q.device.index))
     ws = torch.empty((need,), dtype=torch.uint8, device=q.device)
     rc = h.lib.mpr_debug_scores(h.ptr, _ptr(q), b, _ptr(bank), _ptr(bias), n_local, d, _ptr(scores), _ptr(ws), need,
-                                _stream())
+                                _stream(q.device))
     h.check(rc, "mpr_debug_scores")
     return scores
 
@@ -232,26 +234,69 @@ def exchange_bytes(world: int, cap: int) -> int:
     return int(_native.load().mpr_exchange_bytes(world, cap))
 
 
-def exchange_push(keys: torch.Tensor, rank: int, peer_ptrs, cap: int) -> None:
-    """P2P push of this rank's candidate keys ``[b, kk]`` into every rank's exchange buffer (``peer_ptrs[r]`` = device
-    address of rank r's buffer as mapped on this device)."""
-    h = handle(keys.device.index)
-    assert keys.dtype == torch.int64 and keys.dim() == 2 and keys.is_contiguous()
-    b, kk = keys.shape
-    world = len(peer_ptrs)
-    arr = (C.c_void_p * world)(*[C.c_void_p(int(p)) for p in peer_ptrs])
-    h.check(h.lib.mpr_exchange_push(h.ptr, _ptr(keys), b, kk, rank, world, arr, cap, _stream()), "mpr_exchange_push")
+def retrieve(args: "_native.RetrieveArgs", device: torch.device, io: Optional["_native.HostIO"] = None) -> None:
+    """One retrieval step (``mpr_retrieve`` / ``mpr_retrieve_host``) from a pre-filled argument block: the hot call of
+    :class:`~multimodalpromptretrieval_b200.bank.RetrievalBank` — one ctypes call, normally one kernel launch."""
+    h = handle(device.index)
+    if io is None:
+        h.check(h.lib.mpr_retrieve(h.ptr, C.byref(args), _stream(device)), "mpr_retrieve")
+    else:
+        h.check(h.lib.mpr_retrieve_host(h.ptr, C.byref(args), C.byref(io), _stream(device)), "mpr_retrieve_host")
 
 
-def exchange_merge(my_buf: torch.Tensor, world: int, cap: int, b: int, kk: int
-                   ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-    """Wait for all ``world`` deliveries into ``my_buf`` and merge them into the global top-kk."""
-    h = handle(my_buf.device.index)
-    dev = my_buf.device
-    out_keys = torch.empty((b, kk), dtype=torch.int64, device=dev)
-    out_score = torch.empty((b, kk), dtype=torch.float32, device=dev)
-    out_idx = torch.empty((b, kk), dtype=torch.int32, device=dev)
-    rc = h.lib.mpr_exchange_merge(h.ptr, _ptr(my_buf), world, cap, b, kk, _ptr(out_keys), _ptr(out_score),
-                                  _ptr(out_idx), _stream())
-    h.check(rc, "mpr_exchange_merge")
-    return out_keys, out_score, out_idx
+def debug_counters(device: Optional[int] = None) -> dict:
+    """Scan-kernel event counters since the last call (all zero unless MPR_DEBUG_COUNTERS=1 was set at handle creation)."""
+    h = handle(device)
+    out = (C.c_uint64 * 8)()
+    h.check(h.lib.mpr_debug_counters(h.ptr, out), "mpr_debug_counters")
+    names = ["candidates", "flushes", "slow_groups", "replacements", "warp_tiles", "bound_refreshes"]
+    return {n: int(out[i]) for i, n in enumerate(names)}
+
+
+def debug_timeline(n_ctas: int, device: Optional[int] = None):
+    """Per-CTA event timestamps (ns, relative to the earliest CTA entry) of the last scan launch; see mpr_b200.h."""
+    import numpy as np
+    h = handle(device)
+    out = (C.c_uint64 * (16 * n_ctas))()
+    h.check(h.lib.mpr_debug_timeline(h.ptr, out, n_ctas), "mpr_debug_timeline")
+    a = np.frombuffer(out, dtype=np.uint64).reshape(n_ctas, 16).astype(np.int64)
+    t0 = a[:, 0][a[:, 0] > 0].min() if (a[:, 0] > 0).any() else 0
+    return np.where(a > 0, a - t0, -1)
+
+
+def last_launch_count(device: Optional[int] = None) -> int:
+    h = handle(device)
+    return int(h.lib.mpr_last_launch_count(h.ptr))
+
+
+def set_exchange_timeout(seconds: float, device: Optional[int] = None) -> None:
+    h = handle(device)
+    h.check(h.lib.mpr_set_exchange_timeout(h.ptr, float(seconds)), "mpr_set_exchange_timeout")
+
+
+def embed_prompt(input_ids: torch.Tensor, attention_mask: torch.Tensor, table: torch.Tensor,
+                 image_tokens: Optional[torch.Tensor] = None, length: Optional[int] = None,
+                 mask_dtype: torch.dtype = torch.float32) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Kernel 5: ``input_ids [b, stride]`` (first ``length`` columns) -> ``[b, n_image + length, hidden]`` embeddings
+    with the image tokens prepended, and the concatenated attention mask (float32 as in the reference, or int64)."""
+    h = handle(input_ids.device.index)
+    assert input_ids.dtype == torch.int64 and attention_mask.dtype == torch.int64 and input_ids.dim() == 2
+    assert input_ids.stride(1) == 1 and attention_mask.stride(1) == 1 and input_ids.stride(0) == attention_mask.stride(0)
+    assert table.is_cuda and table.is_contiguous() and table.dim() == 2 and table.dtype in _DTYPES
+    b, stride = input_ids.shape[0], input_ids.stride(0)
+    length = input_ids.shape[1] if length is None else int(length)
+    vocab, hidden = table.shape
+    n_image = 0
+    if image_tokens is not None:
+        assert image_tokens.is_contiguous() and image_tokens.dtype == table.dtype and image_tokens.shape[0] == b and \
+            image_tokens.shape[2] == hidden
+        n_image = image_tokens.shape[1]
+    assert mask_dtype in (torch.float32, torch.int64)
+    dev = input_ids.device
+    out = torch.empty((b, n_image + length, hidden), dtype=table.dtype, device=dev)
+    mask = torch.empty((b, n_image + length), dtype=mask_dtype, device=dev)
+    rc = h.lib.mpr_embed_prompt(h.ptr, _ptr(input_ids), _ptr(attention_mask), b, length, stride, _ptr(table),
+                                _DTYPES[table.dtype], vocab, hidden, _ptr(image_tokens), n_image, _ptr(out), _ptr(mask),
+                                int(mask_dtype == torch.float32), _stream(dev))
+    h.check(rc, "mpr_embed_prompt")
+    return out, mask

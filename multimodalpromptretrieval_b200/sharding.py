@@ -71,23 +71,35 @@ class CandidateExchange:
 
 
 class P2PExchange:
-    """The same exchange without NCCL: every rank stores its candidates straight into every peer's symmetric-memory
-    buffer over NVLink and raises a flag; the merge kernel waits on the flags (csrc/exchange.cuh).  Two launches, no
-    collective library on the data path, epoch kept on the device (CUDA-graph capturable).  With ``world_size == 1`` it
-    degenerates to a self-exchange through an ordinary device buffer (used by the single-GPU tests)."""
+    """Peer-memory candidate exchange: one symmetric-memory buffer per rank, mapped into every peer.  The exchange itself
+    runs inside the retrieval kernel's tail (csrc/tail.cuh): a warp stores its query's candidates straight into every
+    peer's buffer over NVLink, raises a per-query flag, waits for the peers' flags and merges — no collective library on
+    the data path, epoch kept on the device.  This class only owns the buffer and the table of peer pointers the C ABI
+    takes (``mpr_retrieve_args.peer_bufs``).  ``cap`` (>= b * kk of any search) is fixed at construction: growing it
+    would be an implicit collective (rendezvous + barrier) in the middle of a search.
 
-    def __init__(self, device: torch.device, cap: int, group: Optional[dist.ProcessGroup] = None):
+    With ``world_size == 1`` it degenerates to a self-exchange through an ordinary device buffer (single-GPU tests)."""
+
+    def __init__(self, device: torch.device, cap: int, group: Optional[dist.ProcessGroup] = None,
+                 world_size: Optional[int] = None, rank: int = 0):
+        import ctypes as C
         from . import kernels as K
-        self._K = K
         self.cap = int(cap)
-        if dist.is_available() and dist.is_initialized():
+        if world_size is not None:                       # explicit (tests that play a multi-rank exchange on one GPU)
+            self.rank, self.world_size = int(rank), int(world_size)
+            distributed = False
+        elif dist.is_available() and dist.is_initialized():
             self.rank, self.world_size = dist.get_rank(group), dist.get_world_size(group)
+            distributed = self.world_size > 1
         else:
             self.rank, self.world_size = 0, 1
+            distributed = False
         nbytes = K.exchange_bytes(self.world_size, self.cap)
-        if self.world_size == 1:
+        if nbytes == 0:
+            raise ValueError(f"bad exchange geometry world={self.world_size} cap={self.cap}")
+        if not distributed:
             self.buf = torch.zeros(nbytes, dtype=torch.uint8, device=device)
-            self.peer_ptrs = [self.buf.data_ptr()]
+            self.peer_ptrs = [self.buf.data_ptr()] * self.world_size
             self._hdl = None
         else:
             import torch.distributed._symmetric_memory as symm_mem
@@ -97,9 +109,9 @@ class P2PExchange:
             self.peer_ptrs = [int(p) for p in self._hdl.buffer_ptrs]
             torch.cuda.synchronize(device)
             dist.barrier(group)                 # nobody pushes before every buffer is zeroed
+        self.c_ptrs = (C.c_void_p * self.world_size)(*[C.c_void_p(p) for p in self.peer_ptrs])
 
-    def exchange(self, keys: torch.Tensor):
-        b, kk = keys.shape
-        assert b * kk <= self.cap
-        self._K.exchange_push(keys, self.rank, self.peer_ptrs, self.cap)
-        return self._K.exchange_merge(self.buf, self.world_size, self.cap, b, kk)
+    def fill_args(self, args) -> None:
+        """Point a ``RetrieveArgs`` block at this exchange."""
+        args.rank, args.world, args.xchg_cap = self.rank, self.world_size, self.cap
+        args.peer_bufs = self.c_ptrs

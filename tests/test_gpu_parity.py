@@ -388,56 +388,130 @@ def test_create_retrieval_dataset_cache_and_additional_data(tmp_path, golden_cas
     assert b2.retrieve_closest_qa_pairs(batch) == expect
 
 
-def test_cuda_graph_path_matches_eager_and_golden(golden_cases, tokenizer):
-    """The captured search chain (RetrievalBank(use_cuda_graph=True)) returns what the eager launches return, across
-    repeated replays with different query batches."""
+def test_retrieval_step_is_graph_capturable(golden_cases, tokenizer):
+    """A retrieval step (one cooperative launch: scan + tail) captured in a caller's CUDA graph returns what eager
+    launches return, across repeated replays with different query batches."""
     g = golden_cases["k5_train"]
     eager, batch = _bank_from_golden(g, tokenizer)
-    graphed, _ = _bank_from_golden(g, tokenizer, use_cuda_graph=True)
+    graphed, _ = _bank_from_golden(g, tokenizer)
+    skip, kk = 1, g.k + 1
+    img = torch.empty_like(g.q_img, device=dev())
+    txt = torch.empty_like(g.q_txt, device=dev())
+    img.copy_(g.q_img)
+    txt.copy_(g.q_txt)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):                                                 # buffers + workspace zeroing happen outside the capture
+            graphed.run_step(img, txt, None, True, False, kk=kk, skip=skip)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        captured = graphed.run_step(img, txt, None, True, False, kk=kk, skip=skip)["device"]
     for rep in range(3):
-        b2 = dict(batch)
-        b2["image"] = torch.roll(g.q_img, rep, 0).clone()
-        b2["question"] = g.questions[-rep:] + g.questions[:-rep] if rep else list(g.questions)
-        b2["task"] = g.tasks[-rep:] + g.tasks[:-rep] if rep else list(g.tasks)
-        re_, rg = eager._host(eager._retrieve(b2)), graphed._host(graphed._retrieve(b2))
-        assert np.array_equal(re_["idx"], rg["idx"]) and np.array_equal(re_["score"], rg["score"])
-        ids_e, mask_e = eager.retrieve_prompt_ids(b2)
-        ids_g, mask_g = graphed.retrieve_prompt_ids(b2)
-        assert torch.equal(ids_e, ids_g) and torch.equal(mask_e, mask_g)
-        if rep == 0:
-            assert graphed.retrieve_closest_qa_pairs(b2) == g.j["prompts_quant"]
-            assert np.array_equal(ids_g.cpu().numpy(), g.z["input_ids_quant"])
-    assert len(graphed._graphs) == 1
+        qi, qt = torch.roll(g.q_img, rep, 0).to(dev()), torch.roll(g.q_txt, rep, 0).to(dev())
+        img.copy_(qi)
+        txt.copy_(qt)
+        graph.replay()
+        ref = eager.run_step(qi, qt, None, True, False, kk=kk, skip=skip)["device"]
+        for name in ("keys", "idx", "score", "majority_answer", "bucket"):
+            assert torch.equal(captured[name], ref[name]), (rep, name)
+    assert K_handle_ok()
 
 
-@pytest.mark.parametrize("world", [1, 2, 8])
-def test_p2p_exchange_protocol_on_one_gpu(K, world):
-    """The peer-memory exchange (csrc/exchange.cuh), with all `world` ranks played by one GPU IN SEQUENCE (every push is
-    launched before any merge, so no kernel ever waits on a kernel that is not already complete): epochs advance,
-    the double-buffered slots do not mix exchanges, and each rank's merge equals the oracle merge of all lists."""
-    b, kk, cap = 37, 6, 512
+def K_handle_ok():
+    from multimodalpromptretrieval_b200 import kernels
+    return kernels.handle(0).device_error() == 0
+
+
+@pytest.mark.parametrize("world,b", [(2, 37), (8, 37), (8, 300), (2, 300)])
+def test_p2p_exchange_protocol_on_one_gpu(K, world, b):
+    """The peer-memory exchange of the retrieval tail (csrc/tail.cuh) with the OTHER ranks' deliveries pre-populated in
+    the exchange buffer (nothing here ever waits on a kernel that has not finished): rank r of `world` scans its shard,
+    pushes its lists, finds every peer's flags already raised and merges — the result must equal the unsharded search,
+    bit for bit, over several epochs (both slot parities).  (world 2, b 300) is more than one wave of CTAs and takes the
+    two-launch path (stand-alone tail kernel)."""
+    from multimodalpromptretrieval_b200 import _native
+    from multimodalpromptretrieval_b200.sharding import P2PExchange, shard_bounds
+    import ctypes as C
+    n, d, kk = 20011, 256, 6
+    bank = clip_like(n, d, 31)
+    bank[19000] = bank[5]                                                  # duplicate across shards
+    bd = bank.to(dev())
+    _, bias = K.bank_build(bd)
+    cap = 4096
+    me = world // 2
+    x = P2PExchange(dev(), cap, world_size=world, rank=me)
     nbytes = K.exchange_bytes(world, cap)
-    assert nbytes == 1024 + 2 * world * cap * 8
-    bufs = [torch.zeros(nbytes, dtype=torch.uint8, device=dev()) for _ in range(world)]
-    ptrs = [t.data_ptr() for t in bufs]
-    rng = np.random.default_rng(world)
-    for step in range(5):                                                   # several epochs, both parities
-        score = rng.standard_normal((world, b, kk)).astype(np.float32)
-        score[:, :, 0] = 0.25                                               # exact score ties across ranks
-        idx = rng.permutation(world * b * kk).reshape(world, b, kk).astype(np.int32)
-        keys = np.sort(O.keys_from(score, idx), axis=2)[:, :, ::-1].copy()
-        keys_d = [torch.from_numpy(keys[r].view(np.int64)).to(dev()) for r in range(world)]
+    flag_off = 1024
+    slot_off = (flag_off + world * cap * 4 + 15) // 16 * 16
+    assert nbytes == slot_off + 2 * world * cap * 8
+    b0, b1 = shard_bounds(n, me, world)
+    shard, sbias = bd[b0:b1].contiguous(), bias[b0:b1].contiguous()
+    ws = torch.empty(K.search_workspace_bytes(b, b1 - b0, d, kk), dtype=torch.uint8, device=dev())
+    out_keys = torch.empty((b, kk), dtype=torch.int64, device=dev())
+    out_idx = torch.empty((b, kk), dtype=torch.int32, device=dev())
+    status = torch.zeros(4, dtype=torch.int32, device=dev())
+    for epoch in range(1, 4):
+        q = torch.cat([bank[:b // 2].clone(), clip_like(b - b // 2, d, 40 + epoch)]).to(dev())
+        full_keys, _, full_idx = K.search_topk(q, bd, bias, kk)
+        # what the peers would have delivered: their shard's lists into slot[epoch & 1][r], flags = epoch
+        host = x.buf.cpu().numpy().copy()
+        flags = host[flag_off:flag_off + world * cap * 4].view(np.uint32).reshape(world, cap)
+        slots = host[slot_off:].view(np.uint64).reshape(2, world, cap)
         for r in range(world):
-            K.exchange_push(keys_d[r], r, ptrs, cap)
-        ref = O.merge_keys(keys, kk)
-        for r in range(world):
-            ok, osc, oi = K.exchange_merge(bufs[r], world, cap, b, kk)
-            assert np.array_equal(ok.cpu().numpy().view(np.uint64), ref), (step, r)
-            assert np.array_equal(oi.cpu().numpy(), O.decode_keys(ref)[1])
+            if r == me:
+                continue
+            r0, r1 = shard_bounds(n, r, world)
+            k_r, _, _ = K.search_topk(q, bd[r0:r1].contiguous(), bias[r0:r1].contiguous(), kk, idx_base=r0)
+            slots[epoch & 1, r, :b * kk] = k_r.cpu().numpy().view(np.uint64).reshape(-1)
+            flags[r, :b] = epoch
+        x.buf.copy_(torch.from_numpy(host))
+        a = _native.RetrieveArgs()
+        a.q_bf16, a.b, a.bank, a.bias = q.data_ptr(), b, shard.data_ptr(), sbias.data_ptr()
+        a.n_local, a.idx_base, a.d, a.kk = b1 - b0, b0, d, kk
+        a.out_keys, a.out_idx, a.status = out_keys.data_ptr(), out_idx.data_ptr(), status.data_ptr()
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        x.fill_args(a)
+        K.retrieve(a, dev())
+        assert K.last_launch_count() == (1 if K.search_plan(b, b1 - b0, d, kk)["n_ctas"] <= 148 else 2)
+        if (world, b) == (2, 300):
+            assert K.last_launch_count() == 2
+        assert torch.equal(out_keys, full_keys) and torch.equal(out_idx, full_idx), epoch
+        ctrl = x.buf[:8].cpu().numpy().view(np.uint32)
+        assert ctrl[0] == epoch                                            # epoch published by the last warp out
+        assert int(status[0]) == 0
+    assert out_idx[5, :2].tolist() == [5, 19000]
+    assert K.handle(0).device_error() == 0
+
+
+def test_p2p_exchange_times_out_instead_of_hanging(K):
+    """A peer that never delivers: the waiting warps give up after the configured timeout, report
+    MPR_STATUS_XCHG_TIMEOUT in the status word and return the LOCAL result — no trap, no poisoned context."""
+    from multimodalpromptretrieval_b200 import _native
+    from multimodalpromptretrieval_b200.sharding import P2PExchange
+    n, d, b, kk = 3000, 128, 9, 3
+    bank = clip_like(n, d, 1).to(dev())
+    _, bias = K.bank_build(bank)
+    q = clip_like(b, d, 2).to(dev())
+    local_keys, _, _ = K.search_topk(q, bank, bias, kk)
+    x = P2PExchange(dev(), 256, world_size=2, rank=0)
+    ws = torch.empty(K.search_workspace_bytes(b, n, d, kk), dtype=torch.uint8, device=dev())
+    out_keys = torch.empty((b, kk), dtype=torch.int64, device=dev())
+    status = torch.zeros(4, dtype=torch.int32, device=dev())
+    a = _native.RetrieveArgs()
+    a.q_bf16, a.b, a.bank, a.bias, a.n_local, a.d, a.kk = q.data_ptr(), b, bank.data_ptr(), bias.data_ptr(), n, d, kk
+    a.out_keys, a.status, a.workspace, a.workspace_bytes = out_keys.data_ptr(), status.data_ptr(), ws.data_ptr(), ws.numel()
+    x.fill_args(a)
+    K.set_exchange_timeout(0.05)
+    try:
+        K.retrieve(a, dev())
         torch.cuda.synchronize()
-        for r in range(world):
-            ctrl = bufs[r][:8].cpu().numpy().view(np.uint32)
-            assert ctrl[0] == step + 1 and ctrl[1] == 0                    # epoch published, done-counter reset
+    finally:
+        K.set_exchange_timeout(60.0)
+    assert int(status[0]) == _native.STATUS_XCHG_TIMEOUT
+    assert torch.equal(out_keys, local_keys)
     assert K.handle(0).device_error() == 0
 
 
@@ -473,11 +547,13 @@ def test_shard_cache_roundtrip_and_resharding(tmp_path, golden_cases, tokenizer)
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
-@pytest.mark.parametrize("b,d0,d1,kk", [(16, 256, 256, 5), (128, 512, 0, 1), (130, 64, 64, 6), (300, 256, 0, 16)])
+@pytest.mark.parametrize("b,d0,d1,kk", [(16, 256, 256, 5), (128, 512, 0, 1), (130, 64, 64, 6), (300, 256, 0, 16),
+                                        (16, 512, 512, 5), (64, 512, 512, 16), (100, 1024, 0, 2), (7, 1024, 1024, 3),
+                                        (200, 512, 512, 5)])
 def test_fused_query_cast_is_bit_identical_to_two_step(K, dtype, b, d0, d1, kk):
     """N3: concat + bf16 cast of the raw query halves inside the scan kernel's q-tile load == kernel 1 + kernel 2."""
     n, d = 20011, d0 + d1
-    assert K.search_fused_supported(d) and not K.search_fused_supported(1024)
+    assert K.search_fused_supported(d) and K.search_fused_supported(1024) and not K.search_fused_supported(4096)
     bank = clip_like(n, d, 3).to(dev())
     _, bias = K.bank_build(bank)
     g = torch.Generator().manual_seed(b)
@@ -488,6 +564,8 @@ def test_fused_query_cast_is_bit_identical_to_two_step(K, dtype, b, d0, d1, kk):
     keys, score, idx, qb = K.search_topk_fused(a, t, bank, bias, kk, idx_base=7)
     assert torch.equal(keys, keys_ref) and torch.equal(idx, idx_ref) and torch.equal(score, score_ref)
     assert (qb - qbias).abs().max().item() < 1e-3
+    if d > 512:
+        assert torch.equal(qb, qbias)          # the shared-memory q-tile is filled by kernel 1's own row routine
     assert K.handle(0).device_error() == 0
 
 

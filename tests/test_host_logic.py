@@ -102,7 +102,7 @@ def test_c_abi_library_loads_and_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     lib.mpr_abi_version.restype = ctypes.c_int
-    assert lib.mpr_abi_version() == 1
+    assert lib.mpr_abi_version() == _native.ABI_VERSION == 2
 
 
 def test_no_fallback_without_gpu():

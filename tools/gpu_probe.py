@@ -1,5 +1,6 @@
 """First-contact GPU probe: kernels vs plain torch on small shapes, verbose diagnostics (not a test)."""
 import sys, os, time
+import os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from multimodalpromptretrieval_b200 import kernels as K
@@ -56,17 +57,19 @@ def check_topk(b, n, d, kk):
 
 
 t0 = time.time()
-check_build(1000, 512, 0, torch.float32, False)
-check_build(1000, 512, 512, torch.float16, False)
-check_build(777, 256, 256, torch.float32, True)
+QUICK = bool(os.environ.get("PROBE_AB"))
+if not QUICK:
+  check_build(1000, 512, 0, torch.float32, False)
+  check_build(1000, 512, 512, torch.float16, False)
+  check_build(777, 256, 256, torch.float32, True)
 h = K.handle(0)
-for (b, n, d) in [(16, 128, 64), (16, 128, 512), (128, 1000, 512), (5, 300, 1024), (16, 3072, 1024), (200, 5000, 512)]:
+for (b, n, d) in ([] if QUICK else [(16, 128, 64), (16, 128, 512), (128, 1000, 512), (5, 300, 1024), (16, 3072, 1024), (200, 5000, 512)]):
     e = check_scores(b, n, d)
     code = h.device_error()
     if code:
         print("device error code", code, flush=True)
-for (b, n, d, kk) in [(16, 3072, 1024, 1), (16, 14336, 1024, 2), (128, 100000, 512, 5), (1, 50000, 512, 32),
-                      (300, 200000, 512, 16), (64, 1000000, 512, 5)]:
+for (b, n, d, kk) in ([(128, 100000, 512, 32)] if QUICK else [(16, 3072, 1024, 1), (16, 14336, 1024, 2), (128, 100000, 512, 5), (1, 50000, 512, 32),
+                      (300, 200000, 512, 16), (64, 1000000, 512, 5)]):
     check_topk(b, n, d, kk)
     code = h.device_error()
     if code:
@@ -89,12 +92,18 @@ def timing(b, n, d, kk, iters=20):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
     pl = K.search_plan(b, n, d, kk)
+    if os.environ.get("MPR_DEBUG_COUNTERS"):
+        c = K.debug_counters()
+        print("  counters per launch:", {k_: round(v / (iters + 4), 1) for k_, v in c.items()}, flush=True)
     print(f"timing b={b} n={n} d={d} kk={kk}: {ms*1e3:.1f} us/scan  {n*d*2/ms/1e6:.1f} GB/s  "
           f"{2*b*n*d/ms/1e9:.1f} TFLOP/s  {b/ms*1e3:.0f} q/s plan={pl}", flush=True)
 
 import os
 CASES = [(16, 1250000, 512, 5), (128, 1250000, 512, 5), (256, 1250000, 512, 5), (1024, 1048576, 512, 5),
          (4096, 1048576, 512, 5), (128, 10000000, 512, 5)]
+if os.environ.get("PROBE_AB"):
+    CASES = [(128, 1250000, 512, 5), (128, 1250000, 512, 16), (128, 1250000, 512, 32), (16, 1250000, 512, 32),
+             (128, 10000000, 512, 5), (16, 1000000, 1024, 16)]
 if os.environ.get("PROBE_LARGE_K"):
     CASES = [(128, 1250000, 512, 16), (128, 1250000, 512, 32), (16, 1250000, 512, 16), (16, 1000000, 1024, 16)]
 if os.environ.get("PROBE_FULL"):
