@@ -18,8 +18,10 @@ cfg3 = 16 queries x (14 336 + 1 048 576) x 1024, the reference's own row width w
           thread (RetrievalBank.prefetch), every step sees strings never seen before.  e2e.sequential = the same without
           the prefetch, e2e.repeated_questions = an epoch-like run where the question set repeats.
   roofline  the scan kernel (which now contains the whole step): algorithmic bytes (N_local*D*2 + N_local*4) or flops
-          (2*B*N_local*D) / its mean launch time (cudaEvents around the launch via mpr_profile_begin/end, over a region
-          of at least half a second with its own clock samples) against the measured peak in MEASURED_PEAKS.json
+          (2*B*N_local*D) / its mean launch time over THE K timed steps (cudaEvents around every launch on its stream via
+          mpr_profile_begin/end; SM clock / power / throttle reasons polled through NVML every 4 ms) against the measured
+          peak in MEASURED_PEAKS.json; roofline.sustained = the same over a further region of >= 0.6 s, where the GPU
+          sits at its power cap
   cpu_baseline  the reference's torch.cdist + torch.argsort (and north_star's matmul + topk) on the host cores, measured
           on a 1 M-row sample of the bank and scaled by rows (N = 1 only)
   result_digest  CRC of the retrieved rows and of the prompt ids for the fixed query batch: identical at every N
@@ -125,42 +127,80 @@ def workload_config(args, n_gpus):
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
+    """SM clock, power and throttle reasons of one GPU, polled through NVML every few milliseconds on a thread (the timed
+    region of a `--steps 20` run is ~30 ms — shorter than one period of `nvidia-smi -lms`); falls back to nvidia-smi."""
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
-    def __init__(self, gpu_index: int, period_ms: int = 50):
-        self.samples, self.proc, self.thread = [], None, None
+    def __init__(self, gpu_index: int, period_ms: int = 4):
+        self.samples, self.thread, self.proc, self._stop = [], None, None, False
+        self.sm_max = None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.QUERY}",
-                                          "--format=csv,noheader,nounits", "-lms", str(period_ms)],
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it lists indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            phys = gpu_index
+            if vis and all(v.strip().isdigit() for v in vis.split(",")):
+                phys = int(vis.split(",")[gpu_index])
+            h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+
+            def poll():
+                while not self._stop:
+                    try:
+                        sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                        pw = pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0
+                        rs = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                        self.samples.append((time.time(), float(sm), pw, int(rs)))
+                    except Exception:
+                        pass
+                    time.sleep(period_ms / 1000.0)
+
+            self.thread = threading.Thread(target=poll, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.thread = None
+            self._start_smi(gpu_index)
+
+    def _start_smi(self, gpu_index):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+
+            def read():
+                names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+                for line in self.proc.stdout:
+                    try:
+                        r = line.strip().split(", ")
+                        self.sm_max = float(r[1])
+                        bits = sum(self.REASONS[n] for i, n in enumerate(names) if r[3 + i].strip().lower() == "active")
+                        self.samples.append((time.time(), float(r[0]), float(r[2]), bits))
+                    except Exception:
+                        pass
+
+            self.thread = threading.Thread(target=read, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.samples.append((time.time(), line.strip()))
-
     def window(self, t0: float, t1: float):
         """Summary of the samples taken between t0 and t1 (the sampler keeps running)."""
-        if self.proc is None:
-            return None
-        rows = [l.split(", ") for t, l in self.samples if t0 <= t <= t1 + 0.02]
+        rows = [s_ for s_ in self.samples if t0 <= s_[0] <= t1 + 0.002]
         if not rows:
             return None
-        try:
-            sm = sorted(float(r[0]) for r in rows)
-            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-            reasons = [n for i, n in enumerate(names) if any(r[3 + i].strip().lower() == "active" for r in rows)]
-            return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "reasons": reasons,
-                    "power_w_max": max(float(r[2]) for r in rows), "samples": len(rows)}
-        except Exception:
-            return None
+        sm = sorted(r[1] for r in rows)
+        bits = 0
+        for r in rows:
+            bits |= r[3]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_mhz_min": sm[0], "sm_max_mhz": self.sm_max,
+                "reasons": [n for n, m in self.REASONS.items() if bits & m],
+                "power_w_max": max(r[2] for r in rows), "samples": len(rows)}
 
     def stop(self):
+        self._stop = True
         if self.proc is not None:
             self.proc.terminate()
 
@@ -365,14 +405,15 @@ def run_native(args):
               "prompt_ids": zlib.crc32(dv["input_ids"].cpu().numpy().tobytes())}
     sampler = ClockSampler(local_rank) if rank == 0 else None
     warm = max(args.warmup, 3)
-    ms_step, _, (t0, t1) = timed(device_step, args.steps, warm)
+    # THE timed region: W warm-up steps, then exactly K steps; every launch of it is also bracketed by cudaEvents on its
+    # stream (mpr_profile_begin/end) so that the roofline speaks about the same K steps as `value`
+    ms_step, (scan_ms, scan_n, scan_per), (t0, t1) = timed(device_step, args.steps, warm, profile=True)
     clocks = sampler.window(t0, t1) if sampler else None
-    # roofline region: the same step, long enough (>= 0.6 s) for the clock sampler, every launch bracketed by events
-    steps_roof = args.steps if args.quick else min(4000, max(args.steps, int(math.ceil(600.0 / max(ms_step, 1e-3)))))
-    ms_roof, (scan_ms, scan_n, scan_per), (t2, t3) = timed(device_step, steps_roof, 3, profile=True)
-    clocks_roofline = sampler.window(t2, t3) if sampler else None
-    if clocks is None:
-        clocks = clocks_roofline           # the K-step region can be shorter than one nvidia-smi period
+    # sustained region: the same step for >= 0.6 s — a B200 under this load (HBM at full rate with the tensor pipe ~55 %
+    # busy) settles at its 1 kW power cap with SM clocks near 1 GHz, which the ~30 ms region above never reaches
+    steps_sus = args.steps if args.quick else min(4000, max(args.steps, int(math.ceil(600.0 / max(ms_step, 1e-3)))))
+    ms_sus, (sus_ms, sus_n, sus_per), (t2, t3) = timed(device_step, steps_sus, 3, profile=True)
+    clocks_sus = sampler.window(t2, t3) if sampler else None
 
     # ---- end to end: host inputs in, host results out, every step; new question strings every step
     e2e_steps = 20 if args.quick else max(20, min(args.steps, 300))
@@ -434,14 +475,21 @@ def run_native(args):
                 traffic = tj.get("dram_bytes_per_launch")
         except Exception:
             pass
+    per_launch = flops / 1e12 if bound == "tensor" else alg_bytes / 1e9
+    sus_avg_ms = sus_ms / max(sus_n, 1)
+    sus_achieved = per_launch / (sus_avg_ms * 1e-3) if sus_n else 0.0
     roofline = {"bound": bound, "kernel": "scan_topk_kernel (scan + fused tail)", "achieved": achieved, "peak": peak,
                 "unit": runit, "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "algorithmic_flops_per_launch": flops,
                 "avg_launch_ms": scan_avg_ms, "launches_timed": scan_n,
-                "share_of_step": scan_avg_ms / ms_roof if ms_roof else None, "ms_per_step_region": ms_roof,
+                "share_of_step": scan_avg_ms / ms_step if ms_step else None,
                 "launch_ms_min_median_max": [scan_per[0], scan_per[len(scan_per) // 2], scan_per[-1]] if scan_per else None,
-                "clocks": clocks_roofline,
-                "note": "every launch of a >= 0.6 s region bracketed by cudaEvents on its stream (mpr_profile_begin/end)"}
+                "clocks": clocks,
+                "note": "every launch of the K-step timed region bracketed by cudaEvents on its stream (mpr_profile_begin/end)",
+                "sustained": {"achieved": sus_achieved, "frac": sus_achieved / peak, "avg_launch_ms": sus_avg_ms,
+                              "launches_timed": sus_n, "ms_per_step": ms_sus, "seconds": (t3 - t2), "clocks": clocks_sus,
+                              "launch_ms_min_median_max": [sus_per[0], sus_per[len(sus_per) // 2], sus_per[-1]] if sus_per else None,
+                              "note": "the same step back to back for >= 0.6 s: power-capped clocks (see clocks)"}}
 
     # digest of the fixed query batch must not depend on the GPU count (compare with the committed N=1 value)
     expected = None

@@ -60,8 +60,16 @@ int mpr_device_error(mpr_handle_t h, int* code);
 int mpr_bank_build(mpr_handle_t h, const void* src0, int d0, const void* src1, int d1, int src_dtype, int64_t n,
                    int normalise, uint16_t* out_bf16, float* out_bias, void* stream);
 
-/* Bytes of device scratch mpr_search_topk needs for this shape. */
+/*
+ * Bytes of device scratch a search of this shape needs.  The first bytes of a workspace are control words (grid
+ * barrier, tile scheduler, shared admission thresholds) that must be zero when a launch starts: the library zeroes them
+ * (one cudaMemsetAsync) the first time it sees a workspace pointer, and every launch leaves them zero again, so a
+ * workspace that is reused step after step costs nothing.  A caller that lets the memory be used for anything else —
+ * or frees it and may get the same address back from its allocator — must say so with mpr_workspace_invalidate
+ * (workspace == NULL: forget every workspace) before the next search.  One workspace serves one stream at a time.
+ */
 size_t mpr_search_workspace_bytes(mpr_handle_t h, int b, int64_t n_local, int d, int kk);
+int mpr_workspace_invalidate(mpr_handle_t h, const void* workspace);
 
 /*
  * Kernel 2 (+ kernel 4 over the bank splits) — score every query against this shard and keep the best kk rows.
@@ -245,6 +253,33 @@ int mpr_debug_timeline(mpr_handle_t h, uint64_t* out, int n_ctas);
 
 /* Kernel launches issued by the last mpr_retrieve / mpr_retrieve_host on this handle (bench bookkeeping). */
 int mpr_last_launch_count(mpr_handle_t h);
+
+/*
+ * Host-side token cache (no CUDA): builds the per-query prefix CSR (prefix_ids / prefix_off of mpr_retrieve_args) from
+ * cached tokenisations of space-separated chunks.  Replaces the per-batch tokenizer call of
+ * architectures/T5VisionModel.py:161-167 for everything that was seen before; the caller keeps the tokenizer and
+ * registers unseen chunks with mpr_token_cache_put.
+ *   put: registers m chunks at once — chunk j = chunks[chunk_off[j] .. chunk_off[j+1]), its tokens ids[ids_off[j] ..
+ *   ids_off[j+1]).
+ *   assemble: the n texts lie back to back in `texts` (text i = bytes [text_off[i], text_off[i+1]), ASCII).  Row i of the
+ *   CSR = the head head_index[i] of the head table (head_ids / head_off: tokens of "Answer the {task} question:" per
+ *   distinct task; head_index may be NULL) followed by the tokens of every maximal run of non-space bytes of text i.
+ *   out_off [n+1]; out_ids holds out_cap ids (MPR_EWORKSPACE if too small); *longest = the longest row.  Chunks not in the
+ *   cache are reported as (byte offset in `texts`, length) pairs in missing [max_missing][2] and counted in *n_missing;
+ *   the output is complete only when *n_missing == 0.
+ * All functions are thread-safe (one mutex per cache) and never touch the device.
+ */
+typedef struct mpr_token_cache* mpr_token_cache_t;
+int mpr_token_cache_create(mpr_token_cache_t* out);
+int mpr_token_cache_destroy(mpr_token_cache_t c);
+int64_t mpr_token_cache_size(mpr_token_cache_t c);
+int mpr_token_cache_clear(mpr_token_cache_t c);
+int mpr_token_cache_put(mpr_token_cache_t c, int m, const char* chunks, const int32_t* chunk_off, const int32_t* ids,
+                        const int32_t* ids_off);
+int mpr_token_cache_assemble(mpr_token_cache_t c, int n, const char* texts, const int32_t* text_off,
+                             const int32_t* head_ids, const int32_t* head_off, const int32_t* head_index,
+                             int32_t* out_ids, int64_t out_cap, int32_t* out_off, int32_t* missing, int max_missing,
+                             int32_t* n_missing, int32_t* longest);
 
 /*
  * Debug / test aid: the full [b][n_local] score matrix through the SAME tcgen05 pipeline as mpr_search_topk

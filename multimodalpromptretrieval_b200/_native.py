@@ -23,7 +23,9 @@ EXPORTS = [
     "mpr_search_workspace_bytes", "mpr_search_topk", "mpr_merge_topk", "mpr_prompt_gather", "mpr_debug_scores",
     "mpr_search_plan", "mpr_profile_begin", "mpr_profile_end", "mpr_profile_launch_ms", "mpr_exchange_bytes",
     "mpr_search_fused_supported", "mpr_search_topk_fused", "mpr_retrieve", "mpr_retrieve_host",
-    "mpr_set_exchange_timeout", "mpr_embed_prompt", "mpr_last_launch_count", "mpr_debug_counters", "mpr_debug_timeline",
+    "mpr_set_exchange_timeout", "mpr_embed_prompt", "mpr_last_launch_count", "mpr_debug_counters", "mpr_debug_timeline", "mpr_workspace_invalidate",
+    "mpr_token_cache_create", "mpr_token_cache_destroy", "mpr_token_cache_size", "mpr_token_cache_clear",
+    "mpr_token_cache_put", "mpr_token_cache_assemble",
 ]
 
 
@@ -116,6 +118,21 @@ def load() -> C.CDLL:
     lib.mpr_set_exchange_timeout.argtypes = [vp, C.c_double]
     lib.mpr_embed_prompt.restype = i32
     lib.mpr_embed_prompt.argtypes = [vp, vp, vp, i32, i32, i32, vp, i32, i32, i32, vp, i32, vp, vp, i32, vp]
+    lib.mpr_token_cache_create.restype = i32
+    lib.mpr_token_cache_create.argtypes = [C.POINTER(vp)]
+    lib.mpr_token_cache_destroy.restype = i32
+    lib.mpr_token_cache_destroy.argtypes = [vp]
+    lib.mpr_token_cache_size.restype = i64
+    lib.mpr_token_cache_size.argtypes = [vp]
+    lib.mpr_token_cache_clear.restype = i32
+    lib.mpr_token_cache_clear.argtypes = [vp]
+    lib.mpr_token_cache_put.restype = i32
+    lib.mpr_token_cache_put.argtypes = [vp, i32, C.c_char_p, vp, vp, vp]
+    lib.mpr_token_cache_assemble.restype = i32
+    lib.mpr_token_cache_assemble.argtypes = [vp, i32, C.c_char_p, vp, vp, vp, vp, vp, i64, vp, vp, i32, C.POINTER(i32),
+                                             C.POINTER(i32)]
+    lib.mpr_workspace_invalidate.restype = i32
+    lib.mpr_workspace_invalidate.argtypes = [vp, vp]
     lib.mpr_debug_timeline.restype = i32
     lib.mpr_debug_timeline.argtypes = [vp, C.POINTER(C.c_uint64), i32]
     lib.mpr_debug_counters.restype = i32

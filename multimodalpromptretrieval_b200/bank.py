@@ -89,7 +89,7 @@ class _Step:
         need = K.search_workspace_bytes(b, n_local, d, kk, dev.index)
         if need == 0:
             K.search_plan(b, n_local, d, kk, dev.index)          # raises with the library's precise message
-        self.workspace = torch.empty((max(need, 16),), dtype=torch.uint8, device=dev)
+        self.workspace = K.new_workspace(need, dev)
         self.max_len = bank.max_source_length
         # ---- result block layout
         off, lay = 0, {}

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 ROOT = os.path.dirname(PKG)
 OUT = os.path.join(PKG, "lib", "libmpr_b200.so")
-SOURCES = ["mpr_abi.cu"]
+SOURCES = ["mpr_abi.cu", "token_cache.cpp"]
 HEADERS = ["ptx.cuh", "topk_key.cuh", "scan_topk.cuh", "bank_build.cuh", "merge_topk.cuh", "prompt_gather.cuh", "tail.cuh", "embed_gather.cuh",
            os.path.join(ROOT, "include", "mpr_b200.h")]
 

@@ -44,8 +44,9 @@ struct mpr_context {
     int cooperative = 1;                    // fused-tail launches are cooperative (MPR_NO_COOP=1: plain launch)
     int use_reg_list = 1;                   // k + skip <= 8: lists in registers (MPR_NO_REGLIST=1: shared memory)
     unsigned long long xchg_timeout_ns = 60ull * 1000000000ull;
-    const void* ws_ptr = nullptr;           // workspace whose control words are known to be zero ...
-    size_t ws_zeroed = 0;                   // ... over this many leading bytes
+    // workspaces whose control words are known to be zero over `second` leading bytes (the library zeroed them when it
+    // first saw the pointer, every launch leaves them zero); most recently used last, at most 16
+    std::vector<std::pair<const void*, size_t>> clean_ws;
     int last_launches = 0;                  // kernel launches of the last mpr_retrieve
     int prof_used = -1;                     // -1 = profiling off
     int prof_last_n = 0;                    // launches recorded by the last begin/end pair
@@ -288,9 +289,18 @@ static int run_step(mpr_context* h, const mpr_retrieve_args& a, float* dump, cud
     unsigned char* ws = static_cast<unsigned char*>(a.workspace);
     if (!kDump) {
         // control words must be zero before the first launch on this workspace; every launch leaves them zero again
-        if (ws != h->ws_ptr || wl.zero_bytes > h->ws_zeroed) CUDA_TRY(h, cudaMemsetAsync(ws, 0, wl.zero_bytes, st));
-        h->ws_ptr = ws;
-        h->ws_zeroed = wl.zero_bytes;
+        size_t known = 0;
+        for (size_t i = 0; i < h->clean_ws.size(); ++i)
+            if (h->clean_ws[i].first == ws) {
+                known = h->clean_ws[i].second;
+                h->clean_ws.erase(h->clean_ws.begin() + static_cast<long>(i));
+                break;
+            }
+        if (wl.zero_bytes > known) CUDA_TRY(h, cudaMemsetAsync(ws, 0, wl.zero_bytes, st));
+        if (h->clean_ws.size() >= 16) h->clean_ws.erase(h->clean_ws.begin());
+        // after this launch exactly the current shape's control region is guaranteed zero (a larger region of an earlier
+        // shape may since have been used for partial lists)
+        h->clean_ws.emplace_back(ws, wl.zero_bytes);
     }
 
     ScanParams p;
@@ -592,8 +602,7 @@ int mpr_device_error(mpr_handle_t h, int* code) {
     CUDA_TRY(h, cudaMemcpy(code, h->d_err, sizeof(int), cudaMemcpyDeviceToHost));
     if (*code != 0) {
         CUDA_TRY(h, cudaMemset(h->d_err, 0, sizeof(int)));
-        h->ws_ptr = nullptr;          // a starved pipeline may have left the workspace control words dirty
-        h->ws_zeroed = 0;
+        h->clean_ws.clear();          // a starved pipeline may have left the workspace control words dirty
     }
     return MPR_OK;
 }
@@ -643,6 +652,20 @@ int mpr_search_plan(mpr_handle_t h, int b, int64_t n_local, int d, int kk, int* 
 }
 
 int mpr_last_launch_count(mpr_handle_t h) { return h ? h->last_launches : 0; }
+
+int mpr_workspace_invalidate(mpr_handle_t h, const void* workspace) {
+    if (!h) return fail(nullptr, MPR_EINVAL, "null handle");
+    if (!workspace) {
+        h->clean_ws.clear();
+        return MPR_OK;
+    }
+    for (size_t i = 0; i < h->clean_ws.size(); ++i)
+        if (h->clean_ws[i].first == workspace) {
+            h->clean_ws.erase(h->clean_ws.begin() + static_cast<long>(i));
+            break;
+        }
+    return MPR_OK;
+}
 
 int mpr_retrieve(mpr_handle_t h, const mpr_retrieve_args* a, void* stream) {
     if (!h) return fail(nullptr, MPR_EINVAL, "null handle");

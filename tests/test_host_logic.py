@@ -184,3 +184,41 @@ def test_word_cached_tokenisation_equals_direct_tokenisation(tokenizer):
     assert tables.encode_by_words(texts) == ref                  # warm cache
     assert tables.encode_by_words(list(reversed(texts))) == list(reversed(ref))
     assert all(w.isascii() and " " not in w for w in tables._word_cache)
+
+
+def test_native_token_cache_assembly_equals_interpreter_path_and_hf(tokenizer):
+    """csrc/token_cache.cpp (mpr_token_cache_assemble / _put — host code, no GPU): the prefix CSR assembled natively from
+    cached chunk tokenisations == the interpreter's word-cache path == the HF tokenizer on the whole prefix string, for
+    new and repeated questions, empty / space-padded text, both heads; non-ASCII text takes the interpreter path."""
+    import threading
+    from multimodalpromptretrieval_b200 import prompt as P
+    from multimodalpromptretrieval_b200 import synthetic as S
+
+    def tables(native):
+        t = P.PromptTables.__new__(P.PromptTables)
+        t.tokenizer, t.pad_id, t.eos_id = tokenizer, 0, 1
+        t.encode, t._sp = P._fast_encoder(tokenizer)
+        t._task_head, t._word_cache, t._starts_word = {}, {}, None
+        t._native_cache, t._task_index, t._head_table = None, {}, None
+        t._native_lock, t.use_native_cache = threading.Lock(), native
+        return t
+
+    a, b = tables(True), tables(False)
+    tasks = [S.TASKS[i % len(S.TASKS)] for i in range(64)]
+    for rep in range(3):
+        qs = [f"{q} #{rep % 2}-{i}" for i, q in enumerate(S.make_questions(64, 7 + rep % 2))]
+        qs[3], qs[4], qs[5], qs[63] = "  two  spaces here ", "", "x", " trailing "
+        for quant in (True, False):
+            ia, oa = a.prefix_tokens(tasks, qs, quant)
+            ib, ob = b.prefix_tokens(tasks, qs, quant)
+            assert np.array_equal(ia, ib) and np.array_equal(oa, ob)
+            head = "I" if quant else "The"
+            hf = tokenizer([f"Answer the {t} question: " + q + head for t, q in zip(tasks, qs)],
+                           add_special_tokens=False)["input_ids"]
+            assert [ia[oa[i]:oa[i + 1]].tolist() for i in range(64)] == hf
+    assert a._native_cache is not None and _native.load().mpr_token_cache_size(a._native_cache) > 50
+    qs[7] = "où est la lésion ?"
+    ia, oa = a.prefix_tokens(tasks, qs, True)
+    ib, ob = b.prefix_tokens(tasks, qs, True)
+    assert np.array_equal(ia, ib) and np.array_equal(oa, ob)
+    assert a.prefix_tokens([], [], True)[1].tolist() == [0]

@@ -79,7 +79,7 @@ def timing(b, n, d, kk, iters=20):
     q = (torch.randn(b, d, device=dev) * 0.3).to(torch.bfloat16)
     bank = (torch.randn(n, d, device=dev) * 0.3).to(torch.bfloat16)
     bias = -0.5 * (bank.float() ** 2).sum(1)
-    ws = torch.empty(K.search_workspace_bytes(b, n, d, kk), dtype=torch.uint8, device=dev)
+    ws = K.new_workspace(K.search_workspace_bytes(b, n, d, kk), dev)
     ok, os_, oi = K.search_topk(q, bank, bias, kk, workspace=ws)
     for _ in range(3):
         K.search_topk(q, bank, bias, kk, workspace=ws, out_keys=ok, out_score=os_, out_idx=oi)

@@ -21,7 +21,7 @@ tests_all)
   timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -4
   ;;
 bench)
-  timeout 400 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench exit=$?"; tail -3 gpurun_out/bench_n1.err
+  timeout 400 python bench.py ${BENCH_ARGS:-} > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench exit=$?"; tail -3 gpurun_out/bench_n1.err
   python tools/show_bench.py gpurun_out/bench_n1.json
   timeout 400 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref exit=$?"
   python tools/show_bench.py gpurun_out/bench_ref.json

@@ -9,7 +9,7 @@ g = torch.Generator(device=dev).manual_seed(1)
 q = (torch.randn(b, d, device=dev, generator=g) * 0.44).to(torch.bfloat16)
 bank = (torch.randn(n, d, device=dev, generator=g) * 0.44).to(torch.bfloat16)
 _, bias = K.bank_build(bank)
-ws = torch.empty(K.search_workspace_bytes(b, n, d, kk), dtype=torch.uint8, device=dev)
+ws = K.new_workspace(K.search_workspace_bytes(b, n, d, kk), dev)
 for _ in range(3):
     K.search_topk(q, bank, bias, kk, workspace=ws)
 torch.cuda.synchronize()

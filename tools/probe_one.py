@@ -11,7 +11,7 @@ torch.manual_seed(0)
 q = (torch.randn(b, d, device=dev) * 0.3).to(torch.bfloat16)
 bank = (torch.randn(n, d, device=dev) * 0.3).to(torch.bfloat16)
 bias = -0.5 * (bank.float() ** 2).sum(1)
-ws = torch.empty(K.search_workspace_bytes(b, n, d, kk), dtype=torch.uint8, device=dev)
+ws = K.new_workspace(K.search_workspace_bytes(b, n, d, kk), dev)
 ok, os_, oi = K.search_topk(q, bank, bias, kk, workspace=ws)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 torch.cuda.synchronize()
