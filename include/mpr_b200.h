@@ -246,9 +246,10 @@ int mpr_embed_prompt(mpr_handle_t h, const int64_t* input_ids, const int64_t* at
  * the device; returns zeros when the counters are off.
  */
 int mpr_debug_counters(mpr_handle_t h, uint64_t* out8);
-/* With the same switch: out[16*cta + k] = globaltimer (ns) at event k of CTA cta in the LAST scan launch (k: 0 entry,
+/* With the same switch: out[24*cta + k] = globaltimer (ns) at event k of CTA cta in the LAST scan launch (k: 0 entry,
  * 1 q-tile ready, 2 producer done, 3/5 epilogue group 0/1 left its tile loop, 4/6 its partial lists written, 7 CTA done,
- * 8 past the grid barrier, 9 tail done, 10 second tile's data arrived, 11/12 first and 13/14 fourth tile consumed). */
+ * 8 past the grid barrier, 9 tail done, 10 second tile's data arrived, 11/12 first and 13/14 fourth tile consumed,
+ * 15 first tile's accumulator ready, 16-19 its four 32-row chunks done, 20 its buffer released, 21 second tile's bias staged). */
 int mpr_debug_timeline(mpr_handle_t h, uint64_t* out, int n_ctas);
 
 /* Kernel launches issued by the last mpr_retrieve / mpr_retrieve_host on this handle (bench bookkeeping). */

@@ -436,6 +436,10 @@ class RetrievalBank:
             self.is_training_phase = is_training_phase
         if retrieval_k is not None:
             self.retrieval_k = retrieval_k
+        with K.nvtx_range("mpr.bank_build"):
+            self._install_bank(parts, answers, info, answer_ids, answer_strings)
+
+    def _install_bank(self, parts, answers, info, answer_ids, answer_strings) -> None:
         parts = list(parts)
         rows_of = lambda p: p.n_rows if isinstance(p, LazyPart) else int(p[0].shape[0])
         n_total = sum(rows_of(p) for p in parts)
@@ -632,7 +636,7 @@ class RetrievalBank:
         st = self._step(img, txt, kk, skip)
         if self.exchange.world_size > 1 and self.exchange_mode == "nccl":
             return self._run_step_nccl(st, img, txt, prefix, use_quantifier, to_host)
-        with torch.cuda.device(self.device):
+        with torch.cuda.device(self.device), K.nvtx_range("mpr.retrieval_step"):
             return st.run(img, txt, prefix, use_quantifier, to_host)
 
     def _run_step_nccl(self, st: _Step, img, txt, prefix, use_quantifier, to_host) -> Dict[str, object]:
@@ -703,7 +707,8 @@ class RetrievalBank:
             fut = self._prefetched.pop(key, None)
         if fut is not None:
             return fut.result()
-        return self._prompt_tables().prefix_tokens(batch["task"], batch["question"], use_quantifier)
+        with K.nvtx_range("mpr.tokenise"):
+            return self._prompt_tables().prefix_tokens(batch["task"], batch["question"], use_quantifier)
 
     def prefetch(self, batch, use_quantifier: bool = True) -> None:
         """Tokenise the NEXT batch's prefixes on a worker thread while the current step runs on the GPU (they do not
@@ -714,7 +719,11 @@ class RetrievalBank:
             self._pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="mpr-tokenise")
         tables = self._prompt_tables()
         key = (id(batch["question"]), len(batch["question"]), bool(use_quantifier))
-        fut = self._pool.submit(tables.prefix_tokens, batch["task"], batch["question"], use_quantifier)
+        def job(tasks=batch["task"], questions=batch["question"]):
+            with K.nvtx_range("mpr.tokenise_prefetch"):
+                return tables.prefix_tokens(tasks, questions, use_quantifier)
+
+        fut = self._pool.submit(job)
         with self._prefetch_lock:
             if len(self._prefetched) > 8:
                 self._prefetched.clear()

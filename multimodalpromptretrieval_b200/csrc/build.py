@@ -22,12 +22,26 @@ NVCC_FLAGS = [
 ]
 
 
+def _digest() -> str:
+    """Hash of everything the library is built from (sources, headers, flags, compiler path).  A fresh checkout gives
+    every file the same mtime, so staleness is decided by content, not by timestamps."""
+    import hashlib
+    h = hashlib.sha256()
+    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc").encode())
+    deps = [os.path.join(HERE, s) for s in SOURCES] + [x if os.path.isabs(x) else os.path.join(HERE, x) for x in HEADERS]
+    for d in sorted(deps):
+        h.update(os.path.basename(d).encode())
+        with open(d, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def _stale() -> bool:
-    if not os.path.exists(OUT):
+    if not os.path.exists(OUT) or not os.path.exists(OUT + ".sha256"):
         return True
-    t = os.path.getmtime(OUT)
-    deps = [os.path.join(HERE, s) for s in SOURCES] + [h if os.path.isabs(h) else os.path.join(HERE, h) for h in HEADERS]
-    return any(os.path.getmtime(d) > t for d in deps)
+    with open(OUT + ".sha256") as f:
+        return f.read().strip() != _digest()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -42,6 +56,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode != 0:
         raise RuntimeError(f"nvcc failed ({res.returncode}): {' '.join(cmd)}")
+    with open(OUT + ".sha256", "w") as f:
+        f.write(_digest() + "\n")
     return OUT
 
 

@@ -53,7 +53,7 @@ struct mpr_context {
     char err[512] = {0};
 };
 
-constexpr int kDbgWords = 8 + 16 * 2048;   // event counters + a 16-slot timeline for up to 2048 CTAs
+constexpr int kDbgWords = 8 + 24 * 2048;   // event counters + a 24-slot timeline for up to 2048 CTAs
 
 static thread_local char g_err[512] = "";
 
@@ -134,7 +134,7 @@ static int make_plan(mpr_context* h, int b, int64_t n_local, int d, int kk, Scan
         // (deeper pending buffers were measured to HURT: 32 slots -> +25 % at k+s = 16/32, because the admission
         // threshold only moves at a flush and a stale threshold admits many more candidates)
         const int caps1[] = {16, 14, 12, 10, 10}, caps2[] = {16, 14, 12, 10};
-        const int caps0[] = {0};                       // register lists: no pending buffer either
+        const int caps0[] = {16};                      // register lists: only the pending buffer lives in shared memory
         auto units_for = [&](int cap, int groups) {   // 16 KiB ring units left beside the resident q-tile and the lists
             const ScanSmemLayout fixed = scan_smem_layout(pl->n_chunks, pl->q_box_rows, pl->kk_pad, cap, 0, 1, groups);
             return (kMaxSmem - 1024 - static_cast<int>(fixed.total)) / kStageBytes;
@@ -145,7 +145,7 @@ static int make_plan(mpr_context* h, int b, int64_t n_local, int d, int kk, Scan
         const int n_caps = pl->reg_list ? 1 : pl->n_epi_groups == 1 ? 5 : 4;
         pl->cand_cap = caps[n_caps - 1];
         stages = units_for(pl->cand_cap, pl->n_epi_groups);
-        for (int want : {6, 3}) {
+        for (int want : {8, 6, 3}) {     // 128 KiB in flight per SM if any pending depth allows it, else 96, else 48
             bool found = false;
             for (int c = 0; c < n_caps && !found; ++c)
                 if (units_for(caps[c], pl->n_epi_groups) >= want) {
@@ -402,8 +402,8 @@ static int run_step(mpr_context* h, const mpr_retrieve_args& a, float* dump, cud
         ++h->prof_used;
     }
     if (!kDump && !fused_tail) {
-        const int warps_per_block = 4;
-        tail_kernel<<<(b + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(t);
+        const int blocks = b < h->num_sms * 8 ? b : h->num_sms * 8;      // one block per query, grid-stride beyond that
+        tail_kernel<<<blocks, kTailWarps * 32, 0, st>>>(t);
         CUDA_TRY(h, cudaGetLastError());
         ++h->last_launches;
     }
@@ -589,10 +589,10 @@ int mpr_debug_counters(mpr_handle_t h, uint64_t* out8) {
 
 int mpr_debug_timeline(mpr_handle_t h, uint64_t* out, int n_ctas) {
     if (!h || !out || n_ctas < 1 || n_ctas > 2048) return fail(h, MPR_EINVAL, "bad argument");
-    memset(out, 0, sizeof(uint64_t) * 16 * n_ctas);
+    memset(out, 0, sizeof(uint64_t) * 24 * n_ctas);
     if (!h->d_dbg) return MPR_OK;
     DeviceGuard guard(h->device);
-    CUDA_TRY(h, cudaMemcpy(out, h->d_dbg + 8, sizeof(uint64_t) * 16 * n_ctas, cudaMemcpyDeviceToHost));
+    CUDA_TRY(h, cudaMemcpy(out, h->d_dbg + 8, sizeof(uint64_t) * 24 * n_ctas, cudaMemcpyDeviceToHost));
     return MPR_OK;
 }
 

@@ -82,7 +82,7 @@ struct ScanParams {
     const void* qsrc1;     // [b_total][qd1] or nullptr
     int qd0, qd1, q_dtype, q_normalise;
     float* q_bias_out;     // [b_total] -0.5*|bf16(q)|^2 (written by split 0), or nullptr
-    uint64_t* part_keys;   // [b_total][kk][n_splits * kEpiGroups]
+    uint64_t* part_keys;   // [b_total][n_splits * kEpiGroups][kk], each list unordered
     uint32_t* tile_ctr;    // [n_qtiles] dynamic tile scheduler (nullptr: static contiguous ranges)
     uint32_t* gthr;        // [b_total][ns] shared admission thresholds, ordered-u32 scores (nullptr: off)
     int ns;                // threshold slots per query (multiple of 4, >= kk)
@@ -179,9 +179,8 @@ __device__ __forceinline__ float prep_query_row_to_smem(const ScanParams& p, lon
 // kQTmem (D <= 512): the q-tile lives in TENSOR MEMORY (columns [0, D/2)) and is the MMA's TMEM A operand.  Only B then
 // crosses the 128 B/cycle shared-memory port, and the shared memory the q-tile would occupy goes to the bank ring.  The
 // accumulator ring is then 2 x 128 columns at [256, 512).
-// kRegList (k + skip <= 8, the headline k = 5): the per-query list lives in REGISTERS (8 keys, unsorted, minimum tracked):
-// an admitted score replaces the minimum with ~60 register instructions and moves the threshold at once — no pending
-// buffer, no shared-memory latency chain.  Larger k keeps the list in shared memory behind a pending buffer.
+// kRegList (k + skip <= 8, the headline k = 5): the per-query list lives in REGISTERS (the best eight keys, sorted);
+// only the pending buffer stays in shared memory.  Larger k keeps the list in shared memory as well.
 // kFuseQ: see ScanParams::qsrc0 — replaces /root/reference/dataset/VQAFeatureDataset.py:189-191 in-kernel, for the
 // tensor-memory q-tile (each epilogue thread converts its own row) and the shared-memory one (a warp per row, D <= 2048).
 template <bool kDump, int kCluster, bool kQTmem, bool kFuseQ = false, bool kRegList = false>
@@ -252,7 +251,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const uint32_t tmem_base = *tmem_slot;
     // debug timeline (MPR_DEBUG_COUNTERS=1): dbg[8 + 16*cta + k] = globaltimer at event k of this CTA
     auto stamp = [&](int k) {
-        if (p.dbg_ts) p.dbg_ts[16 * blockIdx.x + k] = ptx::globaltimer_ns_fenced();
+        if (p.dbg_ts) p.dbg_ts[24 * blockIdx.x + k] = ptx::globaltimer_ns_fenced();
     };
     if (threadIdx.x == 0) stamp(0);
     const uint32_t crank = kCluster > 1 ? ptx::cluster_ctarank() : 0u;
@@ -439,7 +438,24 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         // The list is kept UNSORTED while the scan runs: an admitted candidate overwrites the current minimum and the new
         // minimum is found by one pass of independent loads (no store chain) — a sorted insert costs a dependent
         // load/compare/store per shifted element, which for k+s = 16..32 was most of the kernel's time (round 1: 43 % /
-        // 24 % of the HBM roofline).  The list is sorted once, when the CTA writes its partial result.
+        // 24 % of the HBM roofline).  It is never sorted here: the tail's pool merge (tail.cuh) takes unordered lists.
+        // register list (kRegList): the query's best EIGHT keys, sorted descending, 0 = empty.  Keeping eight whatever
+        // k + skip <= 8 is makes every index static; the admission threshold is then the 8th best score (a superset of
+        // the top-(k+skip) is kept, the first k+skip are written out).  An insert is position = number of entries above
+        // the key (eight independent compares) followed by eight independent selects: ~90 instructions, depth ~10.
+        uint64_t L[8];
+        if constexpr (kRegList) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) L[j] = 0ull;
+        }
+        auto reg_insert = [&](uint64_t key) {      // caller: key > L[7]
+            int pos = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) pos += L[j] > key ? 1 : 0;
+#pragma unroll
+            for (int j = 7; j >= 1; --j) L[j] = j > pos ? L[j - 1] : (j == pos ? key : L[j]);
+            L[0] = pos == 0 ? key : L[0];
+        };
         int n_list = 0, min_pos = 0;
         uint64_t min_key = 0ull;
 
@@ -459,6 +475,23 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 atomicAdd(p.dbg + 0, static_cast<unsigned long long>(n_pend));
                 if (lane == 0) atomicAdd(p.dbg + 1, 1ull);
             }
+            if constexpr (kRegList) {
+                // each lane folds ITS pending candidates: the loop runs max-over-lanes(n_pend) times, not once per bank row
+                // in which some lane had a candidate (inserting straight from the score loop costs an insert per such row —
+                // nearly every row of the first tiles, ~25 us of ramp-up per launch)
+                for (int c = 0; c < n_pend; ++c) {
+                    const uint2 cand = my_pend[c];
+                    const uint64_t key = make_key(__uint_as_float(cand.x), cand.y);
+                    if (key > L[7]) {
+                        reg_insert(key);
+                        if (p.dbg) atomicAdd(p.dbg + 3, 1ull);
+                    }
+                }
+                n_pend = 0;
+                thr_own = L[7] == 0ull ? -CUDART_INF_F : key_score(L[7]);
+                if (valid) thr = fmaxf(thr_own, thr_shared);
+                return;
+            }
             for (int c = 0; c < n_pend; ++c) {
                 const uint2 cand = my_pend[c];
                 const uint64_t key = make_key(__uint_as_float(cand.x), cand.y);
@@ -475,45 +508,6 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             thr_own = n_list == kk ? key_score(min_key) : -CUDART_INF_F;
             if (valid) thr = fmaxf(thr_own, thr_shared);
         };
-        // register list (kRegList): slots >= kk hold ~0 so that they are never the minimum; 0 = empty = smaller than any key
-        uint64_t L[8];
-        uint64_t rmin_key = 0ull;
-        int rmin_pos = 0;
-        if constexpr (kRegList) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) L[j] = j < kk ? 0ull : ~0ull;
-        }
-        auto reg_insert = [&](float score, uint32_t gidx) {      // caller: score > thr  (=> key > rmin_key)
-            const uint64_t key = make_key(score, gidx);
-            uint64_t mk = ~0ull;
-            int mp = 0;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                L[j] = j == rmin_pos ? key : L[j];
-                if (L[j] < mk) { mk = L[j]; mp = j; }
-            }
-            rmin_key = mk;
-            rmin_pos = mp;
-            thr_own = mk == 0ull ? -CUDART_INF_F : key_score(mk);
-            thr = fmaxf(thr_own, thr_shared);                      // only valid lanes ever get here
-            best = fmaxf(best, score);
-        };
-        // descending selection sort of the n_list live entries; the tail [n_list, kk) stays zero (= empty)
-        auto sort_list = [&]() {
-            for (int i = 0; i + 1 < n_list; ++i) {
-                uint64_t mk = my_list[i];
-                int mp = i;
-                for (int j = i + 1; j < n_list; ++j) {
-                    const uint64_t v = my_list[j];
-                    if (v > mk) { mk = v; mp = j; }
-                }
-                if (mp != i) {
-                    my_list[mp] = my_list[i];
-                    my_list[i] = mk;
-                }
-            }
-        };
-
         if constexpr (kQTmem) {
             // This thread's query row -> its TMEM lane, columns [0, D/2): 8 bf16 (one uint4) fill 4 columns.  The two
             // epilogue groups split the row's 64-element chunks between them (both can reach every lane quadrant).
@@ -662,6 +656,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 float* bias_tile = bias_s + (grp * 2 + ((lt / n_groups) & 1)) * kTileRows;
                 bias_tile[ep_tid] = next_bias;
                 ptx::named_bar_sync(1 + grp, 128);
+                if (done_tiles == 1 && grp == 0 && lane == 0 && quad == 0) stamp(21);
                 {   // the producer is normally a tile or two ahead: fetch the next tile's bias under this tile's work
                     const uint64_t e = tile_ring[(lt + n_groups) & (kTileRing - 1)];
                     have_bias = (e >> 32) == static_cast<uint64_t>(lt + n_groups) + 1ull && static_cast<uint32_t>(e) != kTileEnd;
@@ -721,33 +716,30 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                             if (__any_sync(kFullMask, m > thr)) {
                                 if (p.dbg && lane == 0) atomicAdd(p.dbg + 2, 1ull);
                                 const uint32_t gidx = p.idx_base + row_base + c0 + g * 8;
-                                if constexpr (kRegList) {
 #pragma unroll
-                                    for (int i = 0; i < 8; ++i)
-                                        if (s[i] > thr) reg_insert(s[i], gidx + i);
-                                } else {
-#pragma unroll
-                                    for (int i = 0; i < 8; ++i) {
-                                        if (s[i] > thr) {
-                                            my_pend[n_pend] = make_uint2(__float_as_uint(s[i]), gidx + i);
-                                            ++n_pend;
-                                        }
+                                for (int i = 0; i < 8; ++i) {
+                                    if (s[i] > thr) {
+                                        my_pend[n_pend] = make_uint2(__float_as_uint(s[i]), gidx + i);
+                                        ++n_pend;
                                     }
-                                    if (m > thr) best = fmaxf(best, m);
-                                    if (__any_sync(kFullMask, n_pend > flush_at)) flush();
                                 }
+                                if (m > thr) best = fmaxf(best, m);
+                                if (__any_sync(kFullMask, n_pend > flush_at)) flush();
                             }
                         }
-                        // First tile of a shared-memory list: nothing is known about the query yet and every CTA starts blind
-                        // at the same moment.  Publishing every 32 rows and refreshing before the next 32 lets the ~300
-                        // lists bootstrap one another within the first tile instead of each paying for a full blind tile
-                        // (a blind insert costs hundreds of cycles there; a register-list insert is cheaper than the wait).
-                        if (!kRegList && done_tiles == 0 && my_gthr) refresh_shared();
+                        // First tile of a list: nothing is known about the query yet and every CTA starts blind at the same
+                        // moment.  Every list has published its first 32 rows' maximum before it worked on them, so one
+                        // (blocking, ~1-2 us) refresh after the first 32 rows already yields a bound over ~300 x 32 rows and
+                        // the rest of the tile admits next to nothing; shared-memory lists, whose blind inserts cost
+                        // hundreds of cycles each, refresh after every 32 rows of their first tile.
+                        if (done_tiles == 0 && my_gthr && (!kRegList || c0 == 0)) refresh_shared();
+                        if (done_tiles == 0 && grp == 0 && lane == 0 && quad == 0) stamp(16 + (c0 >> 5));
                     }
                 }
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(bar_tempty(buf));
+                if (done_tiles == 0 && grp == 0 && lane == 0 && quad == 0) stamp(20);
                 if (thr_pending) refresh_consume();
                 if (my_gthr) publish_best();
                 ++done_tiles;
@@ -758,37 +750,24 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         }
 
         if (lane == 0 && quad == 0) stamp(3 + 2 * grp);
-        // partial result of this (split, group, q-tile): part_keys[q0 + row][rank][split * 2 + grp] — rank-major per
-        // query, so the merge's walk over all lists' rank-i candidates is one contiguous stream
+        // partial result of this (split, group, q-tile): part_keys[q0 + row][split * 2 + grp][rank]
         if (warp_has_work) {
+            // list-major: every thread's kk keys are contiguous (one or a few full sectors per thread; rank-major cost a
+            // separate 32-byte sector per 8-byte key — 40 MB of sector writes per launch at k + skip = 32)
             const size_t n_lists = static_cast<size_t>(p.n_splits) * kEpiGroups;
-            uint64_t* dst = p.part_keys + static_cast<size_t>(q0 + row) * kk * n_lists + split * kEpiGroups + grp;
+            uint64_t* dst = p.part_keys + (static_cast<size_t>(q0 + row) * n_lists + split * kEpiGroups + grp) * kk;
             if constexpr (kRegList) {
-                // descending sort of the 8 registers (odd-even transposition network), unused slots sink to the end
-#pragma unroll
-                for (int j = 0; j < 8; ++j) L[j] = (j < kk && active_group) ? L[j] : 0ull;
-#pragma unroll
-                for (int round = 0; round < 8; ++round) {
-#pragma unroll
-                    for (int j = round & 1; j + 1 < 8; j += 2) {
-                        const uint64_t hi = L[j] > L[j + 1] ? L[j] : L[j + 1];
-                        const uint64_t lo = L[j] > L[j + 1] ? L[j + 1] : L[j];
-                        L[j] = hi;
-                        L[j + 1] = lo;
-                    }
-                }
-                if (valid) {
+                if (active_group) flush();
+                if (valid) {                      // the register list is already sorted: its first k + skip entries go out
 #pragma unroll
                     for (int i = 0; i < 8; ++i)
-                        if (i < kk) dst[static_cast<size_t>(i) * n_lists] = L[i];
+                        if (i < kk) dst[i] = active_group ? L[i] : 0ull;
                 }
             } else {
-                if (active_group) {
-                    flush();
-                    sort_list();
-                }
-                if (valid)
-                    for (int i = 0; i < kk; ++i) dst[static_cast<size_t>(i) * n_lists] = active_group ? my_list[i] : 0ull;
+                if (active_group) flush();
+                if (lane == 0 && quad == 0 && grp == 0) stamp(22);
+                if (valid)                       // as it lies (unordered, empty slots are 0): the tail's pool merge needs no order
+                    for (int i = 0; i < kk; ++i) dst[i] = active_group ? my_list[i] : 0ull;
             }
         }
         if (lane == 0 && quad == 0) stamp(4 + 2 * grp);
@@ -828,8 +807,9 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             if (threadIdx.x == 0) stamp(8);
             uint32_t e = 0;
             if (tail.xchg.world > 1) e = *reinterpret_cast<volatile uint32_t*>(tail.xchg.peers.buf[tail.xchg.rank]) + 1u;
-            for (int q = blockIdx.x + gridDim.x * warp; q < tail.b; q += gridDim.x * kScanWarps)
-                warp_tail_query(tail, q, e, lane);
+            // the list memory of the scan is free now: 10 x 32 keys of it carry the warps' partial merges
+            uint64_t* sbuf = reinterpret_cast<uint64_t*>(smem + lay.list_off);
+            for (int q = blockIdx.x; q < tail.b; q += gridDim.x) block_tail_query<kScanWarps>(tail, q, e, sbuf, warp, lane);
             __syncthreads();
             if (threadIdx.x == 0) stamp(9);
             if (threadIdx.x == 0) tail_ticket(tail, e, gridDim.x);

@@ -86,6 +86,54 @@ __device__ __forceinline__ uint64_t warp_merge_lists(const uint64_t* __restrict_
     return elem;
 }
 
+// Top-kk of an UNORDERED pool of m keys (0 = empty), contiguous at `pool`: what the scan's (split, group) lists of one
+// query are.  Two streaming passes: (1) every lane's maximum -> the kk-th largest of the 32 lane maxima is a key that at
+// least kk keys reach, so everything below it is out; (2) the few survivors are inserted into the warp's sorted list.
+// Neither pass depends on the order inside the per-CTA lists, so the scan writes them unsorted, and unlike a rank-by-rank
+// walk over sorted lists there is no chain of dependent L2 round trips (14 us per query at k + skip = 32).
+template <bool kCoherent>
+__device__ __forceinline__ uint64_t warp_merge_pool(const uint64_t* __restrict__ pool, int m, int kk, int lane) {
+    uint64_t lm = 0ull;
+    for (int i0 = 0; i0 < m; i0 += 32 * kMergeUnroll) {
+        uint64_t key[kMergeUnroll];
+#pragma unroll
+        for (int u = 0; u < kMergeUnroll; ++u) {
+            const int i = i0 + u * 32 + lane;
+            key[u] = i < m ? load_key<kCoherent>(pool + i) : 0ull;
+        }
+#pragma unroll
+        for (int u = 0; u < kMergeUnroll; ++u) lm = key[u] > lm ? key[u] : lm;
+    }
+    int rank = 0;
+    for (int o = 1; o < 32; ++o) rank += shfl_u64(lm, (lane + o) & 31) > lm ? 1 : 0;
+    const unsigned who = __ballot_sync(kFullMask, rank == kk - 1 && lm != 0ull);
+    const uint64_t floor = who ? shfl_u64(lm, __ffs(who) - 1) - 1ull : 0ull;
+    uint64_t elem = 0ull, kth = floor;
+    for (int i0 = 0; i0 < m; i0 += 32 * kMergeUnroll) {
+        uint64_t key[kMergeUnroll];
+#pragma unroll
+        for (int u = 0; u < kMergeUnroll; ++u) {
+            const int i = i0 + u * 32 + lane;
+            key[u] = i < m ? load_key<kCoherent>(pool + i) : 0ull;
+        }
+#pragma unroll
+        for (int u = 0; u < kMergeUnroll; ++u) {
+            unsigned pending = __ballot_sync(kFullMask, key[u] > kth);
+            while (pending) {
+                const int src = __ffs(pending) - 1;
+                pending &= pending - 1;
+                const uint64_t cand = shfl_u64(key[u], src);
+                if (cand > kth) {    // uniform: the threshold may have moved since the ballot
+                    elem = warp_list_insert(elem, cand, lane);
+                    const uint64_t last = shfl_u64(elem, kk - 1);
+                    kth = last > floor ? last : floor;
+                }
+            }
+        }
+    }
+    return elem;
+}
+
 __device__ __forceinline__ void store_merged(uint64_t elem, int q, int kk, int lane, uint64_t* out_keys, float* out_score,
                                              int32_t* out_idx) {
     if (lane < kk) {
@@ -284,7 +332,7 @@ __device__ __forceinline__ void warp_vote_and_gather(const PromptParams& p, int 
 //   u32 gthr[b][ns]          shared admission thresholds (see scan_topk.cuh)
 struct TailParams {
     int b, kk;
-    const uint64_t* part_keys;   // [b][kk][n_lists]
+    const uint64_t* part_keys;   // [b][n_lists][kk], each list unordered
     int n_lists;
     uint32_t* ctrl;              // -> arrived, done
     uint32_t* tile_ctr;
@@ -299,19 +347,31 @@ struct TailParams {
     PromptParams prompt;
 };
 
-// Runs the whole tail for query q on one warp.  `e` = exchange epoch of this launch (ignored when world <= 1).
-__device__ __forceinline__ void warp_tail_query(const TailParams& t, int q, uint32_t e, int lane) {
-    const size_t n_lists = static_cast<size_t>(t.n_lists);
-    uint64_t elem = warp_merge_lists<true>(t.part_keys + static_cast<size_t>(q) * t.kk * n_lists, t.n_lists, 1ll,
-                                           static_cast<long long>(n_lists), t.kk, lane);
-    if (t.gthr && lane < t.ns) t.gthr[static_cast<size_t>(q) * t.ns + lane] = 0u;     // leave the thresholds zeroed
-    if (t.xchg.world > 1) elem = warp_exchange(t.xchg, e, elem, q, t.kk, lane, t.status);
-    store_merged(elem, q, t.kk, lane, t.out_keys, t.out_score, t.out_idx);
-    if (t.prompt.answer_id) {
-        const uint64_t src = shfl_u64(elem, min(lane + t.prompt.skip, 31));
-        const int row = (lane < t.kk - t.prompt.skip) ? key_row(src) : -1;
-        warp_vote_and_gather(t.prompt, q, row, lane);
+// Runs the whole tail for query q on one thread block of kWarps warps (every thread of the block must call it): the
+// warps split the query's candidate pool between them (the pool merge is a stream of L2 reads; one warp keeps too few
+// of them in flight), leave their sorted top-kk in shared memory (sbuf: kWarps x 32 keys), and warp 0 merges those and
+// finishes the query.  `e` = exchange epoch of this launch (ignored when world <= 1).
+template <int kWarps>
+__device__ __forceinline__ void block_tail_query(const TailParams& t, int q, uint32_t e, uint64_t* sbuf, int warp, int lane) {
+    const int m = t.n_lists * t.kk;
+    const int per = ((m + kWarps - 1) / kWarps + 31) & ~31;
+    const int lo = min(m, warp * per), hi = min(m, lo + per);
+    const uint64_t* pool = t.part_keys + static_cast<size_t>(q) * m;
+    const uint64_t mine = warp_merge_pool<true>(pool + lo, hi - lo, t.kk, lane);
+    sbuf[warp * 32 + lane] = lane < t.kk ? mine : 0ull;
+    __syncthreads();
+    if (warp == 0) {
+        uint64_t elem = warp_merge_lists<false>(sbuf, kWarps, 32ll, 1ll, t.kk, lane);
+        if (t.gthr && lane < t.ns) t.gthr[static_cast<size_t>(q) * t.ns + lane] = 0u;     // leave the thresholds zeroed
+        if (t.xchg.world > 1) elem = warp_exchange(t.xchg, e, elem, q, t.kk, lane, t.status);
+        store_merged(elem, q, t.kk, lane, t.out_keys, t.out_score, t.out_idx);
+        if (t.prompt.answer_id) {
+            const uint64_t src = shfl_u64(elem, min(lane + t.prompt.skip, 31));
+            const int row = (lane < t.kk - t.prompt.skip) ? key_row(src) : -1;
+            warp_vote_and_gather(t.prompt, q, row, lane);
+        }
     }
+    __syncthreads();
 }
 
 // Completion ticket: the last warp group to finish re-zeroes the control block and publishes the exchange epoch.
@@ -330,14 +390,15 @@ __device__ __forceinline__ void tail_ticket(const TailParams& t, uint32_t e, uin
     }
 }
 
-// Stand-alone tail (multi-launch path: grids larger than one wave cannot hold a grid barrier): one warp per query.
-__global__ void __launch_bounds__(128) tail_kernel(const TailParams t) {
-    const int lane = threadIdx.x & 31;
-    const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+// Stand-alone tail (multi-launch path: grids larger than one wave cannot hold a grid barrier): one block per query.
+constexpr int kTailWarps = 4;
+
+__global__ void __launch_bounds__(kTailWarps * 32) tail_kernel(const TailParams t) {
+    __shared__ uint64_t sbuf[kTailWarps * 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t e = 0;
     if (t.xchg.world > 1) e = *reinterpret_cast<volatile uint32_t*>(t.xchg.peers.buf[t.xchg.rank]) + 1u;
-    if (q < t.b) warp_tail_query(t, q, e, lane);
-    __syncthreads();
+    for (int q = blockIdx.x; q < t.b; q += gridDim.x) block_tail_query<kTailWarps>(t, q, e, sbuf, warp, lane);
     if (threadIdx.x == 0) tail_ticket(t, e, gridDim.x);
 }
 

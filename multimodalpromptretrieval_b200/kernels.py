@@ -5,6 +5,7 @@ torch is plumbing here (device memory + streams); all arithmetic happens in ``li
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -12,6 +13,26 @@ import torch
 from . import _native
 
 _handles = {}
+
+# NVTX ranges around bank build / retrieval step / tokenisation / shard I/O (MPR_NVTX=1): named spans for nsys / ncu
+# timelines.  Off by default — the step's host path is a few tens of microseconds and two extra calls would show.
+_NVTX = os.environ.get("MPR_NVTX", "") == "1"
+
+
+class nvtx_range:
+    __slots__ = ("name",)
+
+    def __init__(self, name: str):
+        self.name = name
+
+    def __enter__(self):
+        if _NVTX:
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        if _NVTX:
+            torch.cuda.nvtx.range_pop()
+        return False
 
 
 def handle(device: Optional[int] = None) -> _native.Handle:
@@ -266,9 +287,9 @@ def debug_timeline(n_ctas: int, device: Optional[int] = None):
     """Per-CTA event timestamps (ns, relative to the earliest CTA entry) of the last scan launch; see mpr_b200.h."""
     import numpy as np
     h = handle(device)
-    out = (C.c_uint64 * (16 * n_ctas))()
+    out = (C.c_uint64 * (24 * n_ctas))()
     h.check(h.lib.mpr_debug_timeline(h.ptr, out, n_ctas), "mpr_debug_timeline")
-    a = np.frombuffer(out, dtype=np.uint64).reshape(n_ctas, 16).astype(np.int64)
+    a = np.frombuffer(out, dtype=np.uint64).reshape(n_ctas, 24).astype(np.int64)
     t0 = a[:, 0][a[:, 0] > 0].min() if (a[:, 0] > 0).any() else 0
     return np.where(a > 0, a - t0, -1)
 

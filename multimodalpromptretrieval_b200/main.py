@@ -124,7 +124,7 @@ class T5RetrievalModel(torch.nn.Module):
     prompt ids → T5.  Image tokens are omitted (CLIP token features are out of scope)."""
 
     def __init__(self, device, tokenizer, retrieval_function=None, retrieval_ids_function=None, use_quantifier=True,
-                 max_source_length=512, max_target_length=128):
+                 max_source_length=512, max_target_length=128, device_embeddings=False):
         super().__init__()
         from transformers import T5Config, T5ForConditionalGeneration
         self.device, self.tokenizer = device, tokenizer
@@ -132,6 +132,15 @@ class T5RetrievalModel(torch.nn.Module):
         self.use_quantifier = use_quantifier
         self.max_source_length, self.max_target_length = max_source_length, max_target_length
         self.T5_model = T5ForConditionalGeneration(T5Config(vocab_size=len(tokenizer), decoder_start_token_id=0))
+        # N4: ids -> T5_model.shared rows on the device (embed.py / kernel 5) instead of handing ids to T5
+        self.device_embeddings = bool(device_embeddings) and retrieval_ids_function is not None
+
+    def _t5_inputs(self, ids, mask):
+        if self.device_embeddings:
+            from .embed import embed_prompt
+            emb, emb_mask = embed_prompt(self.T5_model.shared.weight, ids, mask, None)     # T5VisionModel.py:169,178-180
+            return {"inputs_embeds": emb, "attention_mask": emb_mask}
+        return {"input_ids": ids, "attention_mask": mask}
 
     def prepare_input(self, batch):
         if self.retrieval_ids_function is not None:          # device fast path: ids straight from kernel 3
@@ -151,12 +160,12 @@ class T5RetrievalModel(torch.nn.Module):
         tgt = self.tokenizer(list(batch["answer"]), padding="longest", max_length=self.max_target_length,
                              truncation=True, return_tensors="pt")["input_ids"]
         tgt[tgt == self.tokenizer.pad_token_id] = -100
-        return self.T5_model(input_ids=ids, attention_mask=mask, labels=tgt.to(self.device)).loss
+        return self.T5_model(**self._t5_inputs(ids, mask), labels=tgt.to(self.device)).loss
 
     @torch.no_grad()
     def predict(self, batch):
         ids, mask = self.prepare_input(batch)
-        out = self.T5_model.generate(input_ids=ids, attention_mask=mask, do_sample=False, max_new_tokens=8)
+        out = self.T5_model.generate(**self._t5_inputs(ids, mask), do_sample=False, max_new_tokens=8)
         return self.tokenizer.batch_decode(out, skip_special_tokens=True)
 
 
@@ -246,7 +255,8 @@ def main(argv=None) -> dict:
     model = T5RetrievalModel(device, tokenizer, retrieval_function=retrieval_function,
                              retrieval_ids_function=bank.retrieve_prompt_ids if bank and CFG.get("device_prompt_ids", 1) else None,
                              use_quantifier=use_quantifier, max_source_length=CFG.get("max_source_length", 512),
-                             max_target_length=CFG.get("max_target_length", 128)).to(device)
+                             max_target_length=CFG.get("max_target_length", 128),
+                             device_embeddings=CFG.get("device_prompt_embeddings", 0)).to(device)
     report = {"k": k, "use_quantifier": use_quantifier, "bank_rows": bank.n_total if bank else 0}
 
     if args.train:

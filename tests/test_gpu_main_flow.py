@@ -58,3 +58,15 @@ def test_k_defaults_to_15_when_missing(tmp_path):
     rep = main(["--test", "--config", str(tmp_path / "c2.json")])
     assert rep["k"] == 15 and rep["use_quantifier"] is True                  # main.py:113-116,127-130
     assert all(len(a) == 15 for a in rep["last_batch"]["answers"])
+
+
+def test_train_flow_with_device_embeddings(tmp_path):
+    """N4 in the flow: prompt ids from the retrieval kernel's tail feed kernel 5 (T5 `shared` gather on the device) and T5
+    runs on inputs_embeds; the loss equals the ids-based path's loss (same weights, same batch order), and the gradient
+    reaches `shared` through the host wrapper's index_add backward."""
+    import torch
+    from multimodalpromptretrieval_b200.main import main
+    rep_ids = main(["--train", "--config", _cfg(tmp_path, device_prompt_embeddings=0)])
+    rep_emb = main(["--train", "--config", _cfg(tmp_path, device_prompt_embeddings=1)])
+    assert len(rep_emb["train_losses"]) == 2
+    assert torch.allclose(torch.tensor(rep_ids["train_losses"][:1]), torch.tensor(rep_emb["train_losses"][:1]), rtol=1e-4)
