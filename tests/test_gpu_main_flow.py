@@ -66,7 +66,9 @@ def test_train_flow_with_device_embeddings(tmp_path):
     reaches `shared` through the host wrapper's index_add backward."""
     import torch
     from multimodalpromptretrieval_b200.main import main
-    rep_ids = main(["--train", "--config", _cfg(tmp_path, device_prompt_embeddings=0)])
-    rep_emb = main(["--train", "--config", _cfg(tmp_path, device_prompt_embeddings=1)])
+    (tmp_path / "a").mkdir()
+    (tmp_path / "b").mkdir()                    # separate cache roots: both runs build the bank (same RNG consumption)
+    rep_ids = main(["--train", "--config", _cfg(tmp_path / "a", device_prompt_embeddings=0)])
+    rep_emb = main(["--train", "--config", _cfg(tmp_path / "b", device_prompt_embeddings=1)])
     assert len(rep_emb["train_losses"]) == 2
     assert torch.allclose(torch.tensor(rep_ids["train_losses"][:1]), torch.tensor(rep_emb["train_losses"][:1]), rtol=1e-4)

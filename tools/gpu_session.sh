@@ -36,6 +36,18 @@ ab)
     env ${v//,/ } PROBE_AB=1 timeout 300 python tools/gpu_probe.py 2>&1 | grep -E "timing|error|counters" | cut -c1-200
   done > gpurun_out/ab.log 2>&1; cat gpurun_out/ab.log
   ;;
+sanitize_*)
+  tool=${what#sanitize_}
+  timeout 300 python tools/sanitize_target.py > gpurun_out/sanitize_plain.log 2>&1 &&
+  timeout 1500 compute-sanitizer --tool $tool --log-file gpurun_out/sanitizer_$tool.log python tools/sanitize_target.py > gpurun_out/sanitize_$tool.out 2>&1
+  echo "sanitizer $tool exit=$?"; tail -3 gpurun_out/sanitize_plain.log; tail -5 gpurun_out/sanitizer_$tool.log
+  ;;
+ncu_cfg4)
+  CMD="python bench.py --workload cfg4 --steps 3 --warmup 3 --no-cpu-baseline --quick"
+  timeout 400 $CMD > gpurun_out/plain_cfg4.log 2>&1 &&
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:scan_topk -s 4 -c 1 -o gpurun_out/prof_cfg4 -f $CMD > gpurun_out/ncu_cfg4.log 2>&1
+  echo "ncu cfg4 exit=$?"; python tools/show_bench.py gpurun_out/plain_cfg4.log
+  ;;
 hostprof)
   timeout 300 python tools/profile_host.py 400 2>&1 | head -60
   ;;
