@@ -111,6 +111,7 @@ class _Step:
         self.zero_off = torch.zeros(b + 1, dtype=torch.int32, device=dev)      # "no prefix": vote only
         self.dummy = torch.zeros(16, dtype=torch.int32, device=dev)
         self.h_q = None                                   # pinned staging for pageable host queries
+        self.done_events = [torch.cuda.Event(), torch.cuda.Event()]   # submit(): "result block `turn` is on the host"
         # ---- argument blocks: everything that never changes is filled once
         self.args = _native.RetrieveArgs()
         a = self.args
@@ -196,7 +197,9 @@ class _Step:
     def run(self, img, txt, prefix, use_quantifier: bool, to_host: bool) -> Dict[str, object]:
         """``img`` / ``txt``: query halves, device tensors or (pinned) host tensors; ``prefix`` = None (vote only) or the
         host CSR ``(ids int32, off int32[b+1])`` of the per-query prefix tokens, or device tensors ``(ids, off, longest)``.
-        Returns the result views (device; plus host views when ``to_host``, in which case the call has synchronised)."""
+        Returns the result views (device; plus host views when ``to_host``, in which case the call has synchronised).
+        ``to_host="async"``: the device-to-host copy is queued but NOT awaited; ``out["done"]`` is the event that follows
+        it and ``out["host"]`` must not be read before that event has completed (see :class:`PendingRetrieval`)."""
         bank, a, io = self.bank, self.args, self.io
         dev = bank.device
         turn = self.turn
@@ -263,16 +266,24 @@ class _Step:
         if to_host:
             io.d_out, io.h_out = self._bound_base, self.h_blocks[turn].data_ptr()
             io.out_bytes = self.head_bytes + 2 * self.b * stride * 8
-            io.sync = 1
+            io.sync = 0 if to_host == "async" else 1
         else:
             io.d_out = io.h_out = 0
             io.out_bytes, io.sync = 0, 0
         K.retrieve(a, dev, io)
+        out: Dict[str, object] = {"device": self._cached_views(turn, stride, False), "stride": stride}
+        if to_host == "async":
+            ev = self.done_events[turn]
+            ev.record(torch.cuda.current_stream(dev))
+            if staged_prefix:
+                self.pre_done[turn] = ev
+            out["done"] = ev
+            out["host"] = self._cached_views(turn, stride, True)
+            return out
         if staged_prefix and not to_host:
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(dev))
             self.pre_done[turn] = ev
-        out: Dict[str, object] = {"device": self._cached_views(turn, stride, False), "stride": stride}
         if to_host:
             hv = self._cached_views(turn, stride, True)
             status = int(hv["_status_np"][0])
@@ -281,6 +292,41 @@ class _Step:
                                             f"({'a peer rank did not deliver its candidates in time' if status == _native.STATUS_XCHG_TIMEOUT else 'see mpr_b200.h'})")
             out["host"] = hv
         return out
+
+
+class PendingRetrieval:
+    """A retrieval step that has been queued on the GPU (:meth:`RetrievalBank.submit_prompt_ids_host`): inputs copied in,
+    kernel launched, result copy queued.  :meth:`result` waits for exactly this step and returns what
+    :meth:`RetrievalBank.retrieve_prompt_ids_host` returns.  At most TWO steps of a shape may be outstanding: the result
+    buffers alternate, so the step after next reuses this one's."""
+
+    __slots__ = ("_step", "_done")
+
+    def __init__(self, step: Dict[str, object]):
+        self._step = step
+        self._done = False
+
+    def wait(self) -> Dict[str, torch.Tensor]:
+        """Host views of the whole result block (idx, score, vote, input_ids, ...), valid until the step after next."""
+        host = self._step["host"]
+        if not self._done:
+            self._done = True
+            ev = self._step.get("done")
+            if ev is None:             # the NCCL-exchange path has already synchronised
+                return host
+            ev.synchronize()
+            status = int(host["_status_np"][0])
+            if status != 0:
+                raise K._native.NativeError(
+                    f"retrieval step reported device status {status} "
+                    f"({'a peer rank did not deliver its candidates in time' if status == _native.STATUS_XCHG_TIMEOUT else 'see mpr_b200.h'})")
+        return host
+
+    def result(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        host = self.wait()
+        length = host.get("_length_np")
+        longest_out = int(length.max()) if length is not None else int(host["length"].max())
+        return host["input_ids"][:, :longest_out], host["attention_mask"][:, :longest_out]
 
 
 class RetrievalBank:
@@ -839,3 +885,20 @@ class RetrievalBank:
         length = host.get("_length_np")
         longest_out = int(length.max()) if length is not None else int(host["length"].max())
         return host["input_ids"][:, :longest_out], host["attention_mask"][:, :longest_out]
+
+    def submit_prompt_ids_host(self, batch, use_quantifier: bool = True) -> PendingRetrieval:
+        """Two-deep software pipeline for a host consumer: queues this batch's whole step (host-to-device copy of the
+        embeddings and prefix tokens, the retrieval kernel, the device-to-host copy of the result block) and returns at
+        once; ``.result()`` of the returned handle waits for it.  A training loop that gets batch i+1 from its data loader
+        while batch i is in flight (/root/reference/main.py:176-179) calls ``nxt = submit(batch_{i+1}); ids, mask =
+        cur.result(); cur = nxt`` and the host part of a step hides under the previous step's kernel.  Not memoised; on
+        a sharded bank it is a collective like every search (all ranks submit the same batches in the same order)."""
+        quant = bool(use_quantifier)
+        skip = 1 if self.is_training_phase else 0
+        k = self.retrieval_k
+        self._check_kk(k + skip)
+        with torch.no_grad():
+            img, txt = self._encode(batch)
+        prefix = self._prefix_csr(batch, quant)
+        step = self.run_step(img, txt, prefix, quant, "async", kk=k + skip, skip=skip)
+        return PendingRetrieval(step)

@@ -43,6 +43,8 @@ struct mpr_context {
     int fused_tail = 1;                     // single-wave grids finish the step in the scan launch (MPR_NO_FUSED_TAIL=1)
     int cooperative = 1;                    // fused-tail launches are cooperative (MPR_NO_COOP=1: plain launch)
     int use_reg_list = 1;                   // k + skip <= 8: lists in registers (MPR_NO_REGLIST=1: shared memory)
+    int first_wait_ns = 16000;              // first tile: bounded wait for the shared thresholds (MPR_FIRST_WAIT_NS; -1 = legacy start)
+    int tail_floor = 1;                     // pool merge drops keys below the final shared threshold (MPR_NO_TAIL_FLOOR=1)
     unsigned long long xchg_timeout_ns = 60ull * 1000000000ull;
     // workspaces whose control words are known to be zero over `second` leading bytes (the library zeroed them when it
     // first saw the pointer, every launch leaves them zero); most recently used last, at most 16
@@ -335,6 +337,9 @@ static int run_step(mpr_context* h, const mpr_retrieve_args& a, float* dump, cud
     p.gthr = (!kDump && h->shared_thr) ? reinterpret_cast<uint32_t*>(ws + wl.gthr_off) : nullptr;
     p.ns = wl.ns;
     p.fused_tail = fused_tail ? 1 : 0;
+    // waiting for the slots only pays when every slot is fed by some list that gets a tile right away
+    p.first_wait_ns = (h->first_wait_ns > 0 && (pl.n_splits < wl.ns || pl.n_tiles < 2 * pl.n_splits * pl.n_epi_groups))
+                          ? 0 : h->first_wait_ns;
     p.dbg = h->dbg_counters ? h->d_dbg : nullptr;
     p.dbg_ts = h->d_dbg ? h->d_dbg + 8 : nullptr;
     p.dump = dump;
@@ -351,6 +356,7 @@ static int run_step(mpr_context* h, const mpr_retrieve_args& a, float* dump, cud
     t.n_tile_ctr = pl.n_qtiles;
     t.gthr = p.gthr;
     t.ns = wl.ns;
+    t.use_floor = h->tail_floor;
     t.out_keys = a.out_keys;
     t.out_score = a.out_score;
     t.out_idx = a.out_idx;
@@ -506,6 +512,9 @@ int mpr_create(int device, mpr_handle_t* out) {
         if (flag("MPR_NO_FUSED_TAIL")) h->fused_tail = 0;
         if (flag("MPR_NO_COOP")) h->cooperative = 0;
         if (flag("MPR_NO_REGLIST")) h->use_reg_list = 0;
+        if (flag("MPR_NO_TAIL_FLOOR")) h->tail_floor = 0;
+        const char* fw = getenv("MPR_FIRST_WAIT_NS");
+        if (fw) h->first_wait_ns = atoi(fw) < 0 ? -1 : (atoi(fw) > 100000 ? 100000 : atoi(fw));
         const char* dc = getenv("MPR_DEBUG_COUNTERS");
         h->dbg_counters = dc && dc[0] == '1';
         if (dc && (dc[0] == '1' || dc[0] == '2') && e == cudaSuccess) {

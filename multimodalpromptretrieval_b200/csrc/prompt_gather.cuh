@@ -22,8 +22,9 @@ __global__ void __launch_bounds__(128) prompt_gather_kernel(const PromptParams p
     const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (q >= p.b) return;
     const int k = p.kk - p.skip;
+    const PromptPrefetch f = prompt_prefetch(p, q, lane);
     const int row = lane < k ? p.idx[q * p.kk + p.skip + lane] : -1;
-    warp_vote_and_gather(p, q, row, lane);
+    warp_vote_and_gather(p, q, row, lane, f);
 }
 
 }  // namespace mpr

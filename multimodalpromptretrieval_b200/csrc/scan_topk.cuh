@@ -84,9 +84,12 @@ struct ScanParams {
     float* q_bias_out;     // [b_total] -0.5*|bf16(q)|^2 (written by split 0), or nullptr
     uint64_t* part_keys;   // [b_total][n_splits * kEpiGroups][kk], each list unordered
     uint32_t* tile_ctr;    // [n_qtiles] dynamic tile scheduler (nullptr: static contiguous ranges)
-    uint32_t* gthr;        // [b_total][ns] shared admission thresholds, ordered-u32 scores (nullptr: off)
+    uint32_t* gthr;        // [ns][b_total] shared admission thresholds, ordered-u32 scores (nullptr: off); slot-major so
+                           // that the 32 lanes (= 32 queries) of a warp touch 4 sectors per slot, not 32
     int ns;                // threshold slots per query (multiple of 4, >= kk)
     int fused_tail;        // 1: grid barrier + tail.cuh in this launch (grid must be co-resident)
+    int first_wait_ns;     // first tile of a list: how long to wait for every threshold slot of the query to be filled
+                           // after the tile's maximum was published (0: a single look; < 0: legacy blind-chunk start)
     unsigned long long* dbg;  // debug counters (MPR_DEBUG_COUNTERS=1) or nullptr: [0] candidates admitted, [1] warp flushes,
                            // [2] slow-path 8-groups (per warp), [3] list replacements, [4] warp-tiles, [5] threshold refreshes that found a bound
     unsigned long long* dbg_ts;  // debug timeline (MPR_DEBUG_COUNTERS=1|2) or nullptr: [16 * cta + event]
@@ -594,8 +597,11 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             return (r < static_cast<uint32_t>(p.n_local)) ? __ldg(p.bias + r) : -CUDART_INF_F;   // -inf masks rows past the shard end
         };
         // shared threshold: minimum over this query's ns slots (0 = some slot still empty -> no bound yet)
-        const int my_slot_ = p.gthr ? (split * kEpiGroups + grp) % p.ns : 0;
-        const uint32_t* my_gthr = p.gthr ? p.gthr + static_cast<size_t>(valid ? q0 + row : 0) * p.ns : nullptr;
+        // slot of this list: group 1 is offset by ns/2, so that the group-0 lists ALONE feed every slot — group 0 owns a
+        // CTA's first tile, and its first-tile wait below must not depend on second tiles (one tile time later)
+        const int my_slot_ = p.gthr ? (split + grp * (p.ns >> 1)) % p.ns : 0;
+        const uint32_t* my_gthr = p.gthr ? p.gthr + (valid ? q0 + row : q0) : nullptr;     // slot i at my_gthr[i * b_total]
+        const size_t thr_pitch = static_cast<size_t>(p.b_total);
         auto apply_shared = [&](uint32_t m) {
             // strictly-below-m in the ordered domain: scores >= m stay admissible (their row may still win a tie)
             if (m > 0x00800000u) {
@@ -604,38 +610,34 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 if (p.dbg && valid) atomicAdd(p.dbg + 5, 1ull);
             }
         };
-        auto refresh_shared = [&]() {               // blocking form: one loaded-L2 round trip (1-2 us under a full scan)
+        auto slots_min = [&]() -> uint32_t {        // one loaded-L2 round trip (1-2 us under a full scan)
             uint32_t m = 0xFFFFFFFFu;
-            for (int i = 0; i < p.ns; i += 4) {
-                const uint4 v = __ldcg(reinterpret_cast<const uint4*>(my_gthr + i));
-                m = min(min(m, v.x), min(min(v.y, v.z), v.w));
-            }
-            apply_shared(m);
+#pragma unroll 4
+            for (int i = 0; i < p.ns; ++i) m = min(m, __ldcg(my_gthr + i * thr_pitch));
+            return m;
         };
+        auto refresh_shared = [&]() { apply_shared(slots_min()); };      // blocking form
         // split form: the loads are issued when a tile starts and consumed when it ends, so their latency hides under the
         // tile's own work (a blocking refresh per tile cost ~2 us each during the ramp-up, ~15 us per launch)
-        constexpr int kThrVec = kRegList ? 2 : 8;   // ns / 4 <= 2 for k + skip <= 8, <= 8 in general
-        uint4 thr_pre[kThrVec];
+        constexpr int kThrN = kRegList ? 8 : 32;   // ns <= 8 for k + skip <= 8, <= 32 in general
+        uint32_t thr_pre[kThrN];
         bool thr_pending = false;
         auto refresh_issue = [&]() {
 #pragma unroll
-            for (int i = 0; i < kThrVec; ++i)
-                thr_pre[i] = 4 * i < p.ns ? __ldcg(reinterpret_cast<const uint4*>(my_gthr + 4 * i))
-                                          : make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+            for (int i = 0; i < kThrN; ++i) thr_pre[i] = i < p.ns ? __ldcg(my_gthr + i * thr_pitch) : 0xFFFFFFFFu;
             thr_pending = true;
         };
         auto refresh_consume = [&]() {
             uint32_t m = 0xFFFFFFFFu;
 #pragma unroll
-            for (int i = 0; i < kThrVec; ++i)
-                m = min(min(m, thr_pre[i].x), min(min(thr_pre[i].y, thr_pre[i].z), thr_pre[i].w));
+            for (int i = 0; i < kThrN; ++i) m = min(m, thr_pre[i]);
             apply_shared(m);
             thr_pending = false;
         };
         // publish this list's best score: the minimum over a query's slots bounds its global kk-th best from below
         auto publish_best = [&]() {
             if (valid && best > best_published) {
-                atomicMax(p.gthr + static_cast<size_t>(q0 + row) * p.ns + my_slot_, f32_to_ordered(__float_as_uint(best)));
+                atomicMax(p.gthr + static_cast<size_t>(my_slot_) * p.b_total + q0 + row, f32_to_ordered(__float_as_uint(best)));
                 best_published = best;
             }
         };
@@ -673,15 +675,56 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 
                 if (warp_has_work) {
                     const uint32_t row_base = t * kTileRows;
+                    const uint32_t acc_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + kAccCol0 + buf * kTileRows;
+                    const bool legacy_first = p.first_wait_ns < 0;
+                    bool first_bound = false;      // the wait below ended with every slot filled
+                    if (done_tiles == 0 && my_gthr && !legacy_first) {
+                        // First tile of a list: nothing is known about the query yet, every CTA starts blind at the same
+                        // moment, and a blind row costs an insert.  So the tile is walked TWICE (the accumulators stay in
+                        // tensor memory): pass 1 only takes the maximum of its 128 scores and publishes it; then the warp
+                        // waits — briefly, bounded — until every threshold slot of its queries holds some list's maximum
+                        // (a slot is fed by ~n_lists/ns lists, the earliest one suffices), which bounds the query's kk-th
+                        // best from below by the minimum of ns maxima over >= 128 rows each; pass 2 is the ordinary walk
+                        // and admits a handful of rows instead of all of them.
+                        float cm4[4] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+#pragma unroll 1
+                        for (int c0 = 0; c0 < kTileRows; c0 += 32) {
+                            uint32_t v[32];
+                            ptx::tmem_ld_32x32b_x32(acc_addr + c0, v);
+                            ptx::tmem_wait_ld();
+#pragma unroll
+                            for (int i = 0; i < 32; i += 4) {      // four independent max chains
+                                const float4 bb = *reinterpret_cast<const float4*>(bias_tile + c0 + i);
+                                cm4[0] = fmaxf(cm4[0], __uint_as_float(v[i + 0]) + bb.x);
+                                cm4[1] = fmaxf(cm4[1], __uint_as_float(v[i + 1]) + bb.y);
+                                cm4[2] = fmaxf(cm4[2], __uint_as_float(v[i + 2]) + bb.z);
+                                cm4[3] = fmaxf(cm4[3], __uint_as_float(v[i + 3]) + bb.w);
+                            }
+                        }
+                        const float cm = fmaxf(fmaxf(cm4[0], cm4[1]), fmaxf(cm4[2], cm4[3]));
+                        best = fmaxf(best, cm);
+                        publish_best();
+                        if (grp == 0 && lane == 0 && quad == 0) stamp(23);
+                        const uint64_t w0 = ptx::globaltimer_ns();
+                        for (;;) {
+                            const uint32_t m = slots_min();
+                            const bool filled = !valid || m != 0u;
+                            if (__all_sync(kFullMask, filled)) {
+                                apply_shared(m);
+                                first_bound = true;
+                                break;
+                            }
+                            if (ptx::globaltimer_ns() - w0 >= static_cast<uint64_t>(p.first_wait_ns)) break;
+                        }
+                        if (grp == 0 && lane == 0 && quad == 0) stamp(16);
+                    }
 #pragma unroll 1
                     for (int c0 = 0; c0 < kTileRows; c0 += 32) {
                         uint32_t v[32];
-                        ptx::tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + kAccCol0 +
-                                                    buf * kTileRows + c0, v);
+                        ptx::tmem_ld_32x32b_x32(acc_addr + c0, v);
                         ptx::tmem_wait_ld();
-                        if (done_tiles == 0 && my_gthr) {
-                            // first tile: make this chunk's best score public BEFORE working on it (any real row's score
-                            // is a valid contribution to a slot), so that the other lists' refreshes find it
+                        if (done_tiles == 0 && my_gthr && legacy_first) {
+                            // legacy start: make this chunk's best score public BEFORE working on it
                             float cm = -CUDART_INF_F;
 #pragma unroll
                             for (int i = 0; i < 32; ++i) cm = fmaxf(cm, __uint_as_float(v[i]) + bias_tile[c0 + i]);
@@ -727,13 +770,10 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                                 if (__any_sync(kFullMask, n_pend > flush_at)) flush();
                             }
                         }
-                        // First tile of a list: nothing is known about the query yet and every CTA starts blind at the same
-                        // moment.  Every list has published its first 32 rows' maximum before it worked on them, so one
-                        // (blocking, ~1-2 us) refresh after the first 32 rows already yields a bound over ~300 x 32 rows and
-                        // the rest of the tile admits next to nothing; shared-memory lists, whose blind inserts cost
-                        // hundreds of cycles each, refresh after every 32 rows of their first tile.
-                        if (done_tiles == 0 && my_gthr && (!kRegList || c0 == 0)) refresh_shared();
-                        if (done_tiles == 0 && grp == 0 && lane == 0 && quad == 0) stamp(16 + (c0 >> 5));
+                        // legacy start, and the fallback when the wait above ran out: one blocking refresh after the first
+                        // 32 rows (shared-memory lists, whose blind inserts cost hundreds of cycles each: after every 32)
+                        if (done_tiles == 0 && my_gthr && !first_bound && (!kRegList || c0 == 0)) refresh_shared();
+                        if (done_tiles == 0 && grp == 0 && lane == 0 && quad == 0) stamp(17 + min(c0 >> 5, 2));
                     }
                 }
                 ptx::tc_fence_before();

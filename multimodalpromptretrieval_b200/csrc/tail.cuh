@@ -91,31 +91,20 @@ __device__ __forceinline__ uint64_t warp_merge_lists(const uint64_t* __restrict_
 // least kk keys reach, so everything below it is out; (2) the few survivors are inserted into the warp's sorted list.
 // Neither pass depends on the order inside the per-CTA lists, so the scan writes them unsorted, and unlike a rank-by-rank
 // walk over sorted lists there is no chain of dependent L2 round trips (14 us per query at k + skip = 32).
+// `floor0`: a key known to lie below the pool's kk-th best (0 = none), e.g. from the scan's shared thresholds; with one
+// the pivot pass is skipped for kk > 8, where the kk-th largest of 32 lane maxima is a weak pivot anyway.
 template <bool kCoherent>
-__device__ __forceinline__ uint64_t warp_merge_pool(const uint64_t* __restrict__ pool, int m, int kk, int lane) {
-    uint64_t lm = 0ull;
-    for (int i0 = 0; i0 < m; i0 += 32 * kMergeUnroll) {
-        uint64_t key[kMergeUnroll];
-#pragma unroll
-        for (int u = 0; u < kMergeUnroll; ++u) {
-            const int i = i0 + u * 32 + lane;
-            key[u] = i < m ? load_key<kCoherent>(pool + i) : 0ull;
-        }
-#pragma unroll
-        for (int u = 0; u < kMergeUnroll; ++u) lm = key[u] > lm ? key[u] : lm;
-    }
-    int rank = 0;
-    for (int o = 1; o < 32; ++o) rank += shfl_u64(lm, (lane + o) & 31) > lm ? 1 : 0;
-    const unsigned who = __ballot_sync(kFullMask, rank == kk - 1 && lm != 0ull);
-    const uint64_t floor = who ? shfl_u64(lm, __ffs(who) - 1) - 1ull : 0ull;
-    uint64_t elem = 0ull, kth = floor;
-    for (int i0 = 0; i0 < m; i0 += 32 * kMergeUnroll) {
-        uint64_t key[kMergeUnroll];
-#pragma unroll
-        for (int u = 0; u < kMergeUnroll; ++u) {
-            const int i = i0 + u * 32 + lane;
-            key[u] = i < m ? load_key<kCoherent>(pool + i) : 0ull;
-        }
+__device__ __forceinline__ uint64_t warp_merge_pool(const uint64_t* __restrict__ pool, int m, int kk, int lane,
+                                                    uint64_t floor0 = 0ull) {
+    uint64_t floor = floor0;
+    const bool want_pivot = floor0 == 0ull || kk <= 8;
+    auto pivot_of = [&](uint64_t lm) -> uint64_t {      // the kk-th largest of the 32 lane maxima, minus one
+        int rank = 0;
+        for (int o = 1; o < 32; ++o) rank += shfl_u64(lm, (lane + o) & 31) > lm ? 1 : 0;
+        const unsigned who = __ballot_sync(kFullMask, rank == kk - 1 && lm != 0ull);
+        return who ? shfl_u64(lm, __ffs(who) - 1) - 1ull : 0ull;
+    };
+    auto insert_batch = [&](const uint64_t (&key)[kMergeUnroll], uint64_t& elem, uint64_t& kth) {
 #pragma unroll
         for (int u = 0; u < kMergeUnroll; ++u) {
             unsigned pending = __ballot_sync(kFullMask, key[u] > kth);
@@ -130,6 +119,51 @@ __device__ __forceinline__ uint64_t warp_merge_pool(const uint64_t* __restrict__
                 }
             }
         }
+    };
+    if (m <= 32 * kMergeUnroll) {
+        // the whole pool fits the warp's registers: ONE round of loads serves the pivot and the inserts (the headline
+        // shape, 296 lists x 5 keys over ten warps, is 160 keys per warp)
+        uint64_t key[kMergeUnroll];
+#pragma unroll
+        for (int u = 0; u < kMergeUnroll; ++u) {
+            const int i = u * 32 + lane;
+            key[u] = i < m ? load_key<kCoherent>(pool + i) : 0ull;
+        }
+        if (want_pivot) {
+            uint64_t lm = key[0];
+#pragma unroll
+            for (int u = 1; u < kMergeUnroll; ++u) lm = key[u] > lm ? key[u] : lm;
+            const uint64_t pivot = pivot_of(lm);
+            floor = pivot > floor ? pivot : floor;
+        }
+        uint64_t elem = 0ull, kth = floor;
+        insert_batch(key, elem, kth);
+        return elem;
+    }
+    if (want_pivot) {
+        uint64_t lm = 0ull;
+        for (int i0 = 0; i0 < m; i0 += 32 * kMergeUnroll) {
+            uint64_t key[kMergeUnroll];
+#pragma unroll
+            for (int u = 0; u < kMergeUnroll; ++u) {
+                const int i = i0 + u * 32 + lane;
+                key[u] = i < m ? load_key<kCoherent>(pool + i) : 0ull;
+            }
+#pragma unroll
+            for (int u = 0; u < kMergeUnroll; ++u) lm = key[u] > lm ? key[u] : lm;
+        }
+        const uint64_t pivot = pivot_of(lm);
+        floor = pivot > floor ? pivot : floor;
+    }
+    uint64_t elem = 0ull, kth = floor;
+    for (int i0 = 0; i0 < m; i0 += 32 * kMergeUnroll) {
+        uint64_t key[kMergeUnroll];
+#pragma unroll
+        for (int u = 0; u < kMergeUnroll; ++u) {
+            const int i = i0 + u * 32 + lane;
+            key[u] = i < m ? load_key<kCoherent>(pool + i) : 0ull;
+        }
+        insert_batch(key, elem, kth);
     }
     return elem;
 }
@@ -263,8 +297,27 @@ struct PromptParams {
     int32_t* ret_answer;        // [b][k] answer ids in rank order (or nullptr)
 };
 
+// Everything the prompt stage reads that does NOT depend on the vote, fetched up front so that it is in flight while the
+// lists are merged: the query's prefix range, the offsets of the constant / bucket segments (lane i: seg_off[i], i <= 8)
+// and the bucket-table row for a full vote (lane c: lut[k*(k+1) + c]).  What remains behind the vote is the chain
+// answer_id[row] -> seg_off[answer] -> token ids.
+struct PromptPrefetch {
+    int pre0, pre1, seg, lut_full;
+};
+
+__device__ __forceinline__ PromptPrefetch prompt_prefetch(const PromptParams& p, int q, int lane) {
+    PromptPrefetch f;
+    const int k = p.kk - p.skip;
+    f.pre0 = p.prefix_off[q];
+    f.pre1 = p.prefix_off[q + 1];
+    f.seg = lane <= kSegAnswer0 ? p.seg_off[lane] : 0;
+    f.lut_full = lane <= k ? p.bucket_lut[k * (k + 1) + lane] : 0;
+    return f;
+}
+
 // `row` = bank row retrieved at rank skip + lane (lanes >= k: ignored), -1 = none.
-__device__ __forceinline__ void warp_vote_and_gather(const PromptParams& p, int q, int row, int lane) {
+__device__ __forceinline__ void warp_vote_and_gather(const PromptParams& p, int q, int row, int lane,
+                                                     const PromptPrefetch& f) {
     const int k = p.kk - p.skip;
     // ---- gather the answers of the retrieved rows   (VQAFeatureDataset.py:199)
     int a = -1;
@@ -282,11 +335,12 @@ __device__ __forceinline__ void warp_vote_and_gather(const PromptParams& p, int 
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) rank_key = max(rank_key, __shfl_xor_sync(kFullMask, rank_key, o));
     int maj = -1, cnt = 0, bkt = 0;
-    if (rank_key >= 0) {
+    if (rank_key >= 0) {      // warp-uniform
         cnt = rank_key >> 6;
         const int first = 63 - (rank_key & 63);
         maj = __shfl_sync(kFullMask, a, first);
-        bkt = p.bucket_lut[n_votes * (k + 1) + cnt];      // :223-226
+        // :223-226; the row for n_votes == k is already in registers (cnt <= k <= 31)
+        bkt = (n_votes == k && cnt < 32) ? __shfl_sync(kFullMask, f.lut_full, cnt) : p.bucket_lut[n_votes * (k + 1) + cnt];
     }
     if (lane == 0) {
         p.maj_answer[q] = maj;
@@ -295,11 +349,14 @@ __device__ __forceinline__ void warp_vote_and_gather(const PromptParams& p, int 
     }
 
     // ---- token assembly: prefix | const | [bucket] | answer | </s> | pad...   (:228,230; T5VisionModel.py:153-167)
-    const int pre0 = p.prefix_off[q], len_pre = p.prefix_off[q + 1] - pre0;
+    const int pre0 = f.pre0, len_pre = f.pre1 - f.pre0;
     const int seg_c = p.use_quantifier ? kSegQuant : kSegPlain;
-    const int c0 = p.seg_off[seg_c], len_c = p.seg_off[seg_c + 1] - c0;
+    const int c0 = __shfl_sync(kFullMask, f.seg, seg_c), len_c = __shfl_sync(kFullMask, f.seg, seg_c + 1) - c0;
     int b0 = 0, len_b = 0;
-    if (p.use_quantifier) { b0 = p.seg_off[kSegBucket0 + bkt]; len_b = p.seg_off[kSegBucket0 + bkt + 1] - b0; }
+    {
+        const int bs = __shfl_sync(kFullMask, f.seg, kSegBucket0 + bkt), be = __shfl_sync(kFullMask, f.seg, kSegBucket0 + bkt + 1);
+        if (p.use_quantifier) { b0 = bs; len_b = be - bs; }
+    }
     int a0 = 0, len_a = 0;
     if (maj >= 0) { a0 = p.seg_off[kSegAnswer0 + maj]; len_a = p.seg_off[kSegAnswer0 + maj + 1] - a0; }
     const int body = min(len_pre + len_c + len_b + len_a, p.max_len - 1);   // HF truncation keeps room for </s>
@@ -329,7 +386,7 @@ __device__ __forceinline__ void warp_vote_and_gather(const PromptParams& p, int 
 //   u32 arrived     grid barrier of the fused tail / nothing in the multi-launch path
 //   u32 done        tail completion tickets
 //   u32 tile_ctr[n_qtiles]   dynamic tile scheduler, one counter per q-tile
-//   u32 gthr[b][ns]          shared admission thresholds (see scan_topk.cuh)
+//   u32 gthr[ns][b]          shared admission thresholds, slot-major (see scan_topk.cuh)
 struct TailParams {
     int b, kk;
     const uint64_t* part_keys;   // [b][n_lists][kk], each list unordered
@@ -337,8 +394,9 @@ struct TailParams {
     uint32_t* ctrl;              // -> arrived, done
     uint32_t* tile_ctr;
     int n_tile_ctr;
-    uint32_t* gthr;              // [b][ns]
+    uint32_t* gthr;              // [ns][b]
     int ns;
+    int use_floor;               // pool merge: keys below the scan's final shared threshold are dropped unseen
     uint64_t* out_keys;          // [b][kk] (each may be nullptr)
     float* out_score;
     int32_t* out_idx;
@@ -357,18 +415,29 @@ __device__ __forceinline__ void block_tail_query(const TailParams& t, int q, uin
     const int per = ((m + kWarps - 1) / kWarps + 31) & ~31;
     const int lo = min(m, warp * per), hi = min(m, lo + per);
     const uint64_t* pool = t.part_keys + static_cast<size_t>(q) * m;
-    const uint64_t mine = warp_merge_pool<true>(pool + lo, hi - lo, t.kk, lane);
+    PromptPrefetch pf = {0, 0, 0, 0};
+    if (warp == 0 && t.prompt.answer_id) pf = prompt_prefetch(t.prompt, q, lane);
+    // The scan's shared thresholds end as ns >= kk maxima over disjoint row sets: kk distinct rows score at least their
+    // minimum, so a key whose score is strictly below it cannot be among the query's top kk (ties stay in).
+    uint64_t floor0 = 0ull;
+    if (t.gthr && t.use_floor) {
+        uint32_t mn = lane < t.ns ? __ldcg(t.gthr + static_cast<size_t>(lane) * t.b + q) : 0xFFFFFFFFu;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mn = min(mn, __shfl_xor_sync(kFullMask, mn, o));
+        if (mn > 0x00800000u) floor0 = (static_cast<uint64_t>(mn) << 32) - 1ull;
+    }
+    const uint64_t mine = warp_merge_pool<true>(pool + lo, hi - lo, t.kk, lane, floor0);
     sbuf[warp * 32 + lane] = lane < t.kk ? mine : 0ull;
     __syncthreads();
     if (warp == 0) {
         uint64_t elem = warp_merge_lists<false>(sbuf, kWarps, 32ll, 1ll, t.kk, lane);
-        if (t.gthr && lane < t.ns) t.gthr[static_cast<size_t>(q) * t.ns + lane] = 0u;     // leave the thresholds zeroed
+        if (t.gthr && lane < t.ns) t.gthr[static_cast<size_t>(lane) * t.b + q] = 0u;     // leave the thresholds zeroed
         if (t.xchg.world > 1) elem = warp_exchange(t.xchg, e, elem, q, t.kk, lane, t.status);
         store_merged(elem, q, t.kk, lane, t.out_keys, t.out_score, t.out_idx);
         if (t.prompt.answer_id) {
             const uint64_t src = shfl_u64(elem, min(lane + t.prompt.skip, 31));
             const int row = (lane < t.kk - t.prompt.skip) ? key_row(src) : -1;
-            warp_vote_and_gather(t.prompt, q, row, lane);
+            warp_vote_and_gather(t.prompt, q, row, lane, pf);
         }
     }
     __syncthreads();

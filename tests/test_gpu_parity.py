@@ -338,6 +338,40 @@ def test_retrieval_bank_reproduces_reference_golden(name, golden_cases, tokenize
     assert bank._retrieve(batch) is r
 
 
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_host_api_and_two_deep_pipeline_reproduce_reference_golden(name, golden_cases, tokenizer):
+    """The host-consumer entry points (one mpr_retrieve_host call per step: copy in, step, copy out): the blocking call
+    and the two-deep submit()/result() pipeline return the token ids the reference's tokenizer call produces
+    (T5VisionModel.py:153-167), for host-resident (pinned and pageable) query embeddings."""
+    g = golden_cases[name]
+    bank, batch = _bank_from_golden(g, tokenizer, memoise=False)
+    ids_dev, mask_dev = bank.retrieve_prompt_ids(batch)
+    want_ids, want_mask = ids_dev.cpu(), mask_dev.cpu()
+    s_ref = O.scores_f64(g.queries(), g.bank())
+    skip = 1 if g.training else 0
+    r = bank._host(bank._retrieve(batch))
+    _, tolerated = O.check_index_parity(r["idx"][:, skip:skip + g.k].astype(np.int64), s_ref,
+                                        g.z["top_idx"].astype(np.int64), TOL)
+    if tolerated == 0:
+        assert np.array_equal(want_ids.numpy(), g.z["input_ids_quant"])
+    ids_h, mask_h = bank.retrieve_prompt_ids_host(batch)
+    assert torch.equal(ids_h, want_ids) and torch.equal(mask_h, want_mask)
+    # pipeline: three batches in flight two at a time, quantifier setting alternating; results in submission order
+    quants = [True, False, True]
+    want = [tuple(t.cpu() for t in bank.retrieve_prompt_ids(batch, use_quantifier=q_)) for q_ in quants]
+    bank.prefetch(batch, quants[0])
+    cur = bank.submit_prompt_ids_host(batch, use_quantifier=quants[0])
+    got = []
+    for q_ in quants[1:]:
+        nxt = bank.submit_prompt_ids_host(batch, use_quantifier=q_)
+        got.append(tuple(t.clone() for t in cur.result()))
+        cur = nxt
+    got.append(tuple(t.clone() for t in cur.result()))
+    for (gi, gm), (wi, wm) in zip(got, want):
+        assert torch.equal(gi, wi) and torch.equal(gm, wm)
+    assert cur.wait()["idx"].shape == (g.b, g.k + skip)
+
+
 def test_create_retrieval_dataset_cache_and_additional_data(tmp_path, golden_cases, tokenizer):
     """A1/A2: build from a loader, write the reference-format cache, reload from it, and append the additional
     (ROCO-style) bank — the path that crashes in the reference (VQAFeatureDataset.py:181)."""

@@ -26,7 +26,7 @@ if os.environ.get("MPR_DEBUG_COUNTERS"):
     pl = K.search_plan(b, n, d, kk)
     tl = K.debug_timeline(pl["n_ctas"]) / 1e3          # us
     names = ["entry", "q_ready", "producer_done", "g0_loop_end", "g0_written", "g1_loop_end", "g1_written", "cta_done",
-             "past_grid_barrier", "tail_done", "tile1_data", "g0_tile1", "g1_tile1", "g0_tile4", "g1_tile4", "g0_tile0_ready", "t0_chunk0", "t0_chunk1", "t0_chunk2", "t0_chunk3", "t0_released", "t1_bias_staged", "g0_final_flush_done"]
+             "past_grid_barrier", "tail_done", "tile1_data", "g0_tile1", "g1_tile1", "g0_tile4", "g1_tile4", "g0_tile0_ready", "t0_bound_ready", "t0_chunk0", "t0_chunk1", "t0_chunk3", "t0_released", "t1_bias_staged", "g0_final_flush_done", "t0_published"]
     for k, nm in enumerate(names):
         col = tl[:, k]
         col = col[col >= 0]
