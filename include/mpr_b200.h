@@ -217,6 +217,14 @@ typedef struct mpr_host_io {
     void* h_out;               /* pinned host result block                           */
     size_t out_bytes;
     int sync;
+    /* Optional copy streams (cudaStream_t; NULL = everything on `stream`).  With stream_in the host-to-device copies
+     * run on it and the step on `stream` waits for them; with stream_out the device-to-host copy runs on it after the
+     * step.  A caller that keeps two steps in flight (staging and result buffers alternating) thereby overlaps step
+     * i+1's input copy and step i-1's result copy with step i's kernel.  sync then waits on stream_out.  The caller
+     * owns the ordering of buffer reuse: a staging / result buffer may be handed to a new call only after the call
+     * that last used it has completed (e.g. an event recorded on stream_out). */
+    void* stream_in;
+    void* stream_out;
 } mpr_host_io;
 
 int mpr_retrieve_host(mpr_handle_t h, const mpr_retrieve_args* a, const mpr_host_io* io, void* stream);

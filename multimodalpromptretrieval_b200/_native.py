@@ -53,7 +53,7 @@ class HostIO(C.Structure):
     _fields_ = [
         ("h_q0", C.c_void_p), ("h_q1", C.c_void_p), ("h_prefix_ids", C.c_void_p), ("n_prefix_ids", C.c_int),
         ("h_prefix_off", C.c_void_p), ("d_out", C.c_void_p), ("h_out", C.c_void_p), ("out_bytes", C.c_size_t),
-        ("sync", C.c_int),
+        ("sync", C.c_int), ("stream_in", C.c_void_p), ("stream_out", C.c_void_p),
     ]
 
 

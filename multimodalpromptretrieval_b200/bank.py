@@ -82,8 +82,9 @@ class _Step:
         self.bank, self.b, self.d0, self.d1, self.dtype, self.kk, self.skip = bank, b, d0, d1, dtype, kk, skip
         self.k = k = kk - skip
         d = d0 + d1
-        self.q0 = torch.empty((b, d0), dtype=dtype, device=dev)
-        self.q1 = torch.empty((b, d1), dtype=dtype, device=dev) if d1 else None
+        # device staging for host-resident query halves, one pair per turn (a queued step reads its own pair)
+        self.q0 = [torch.empty((b, d0), dtype=dtype, device=dev) for _ in range(2)]
+        self.q1 = [torch.empty((b, d1), dtype=dtype, device=dev) if d1 else None for _ in range(2)]
         self.q_scratch = torch.empty((b, d), dtype=torch.bfloat16, device=dev) if d > 512 and b > 128 else None
         n_local = bank.retrieval_embeddings.shape[0]
         need = K.search_workspace_bytes(b, n_local, d, kk, dev.index)
@@ -110,8 +111,11 @@ class _Step:
         self.pre_done = [None, None]
         self.zero_off = torch.zeros(b + 1, dtype=torch.int32, device=dev)      # "no prefix": vote only
         self.dummy = torch.zeros(16, dtype=torch.int32, device=dev)
-        self.h_q = None                                   # pinned staging for pageable host queries
+        self.h_q = [None, None]                           # pinned staging for pageable host queries, per turn
         self.done_events = [torch.cuda.Event(), torch.cuda.Event()]   # submit(): "result block `turn` is on the host"
+        self.in_flight = [False, False]                   # a submitted step still owns this turn's buffers
+        self.stage_busy = [None, None]                    # event after a non-blocking step that read this turn's staging
+        self.gen = [0, 0]                                 # submissions per turn (a stale handle must not release a newer step)
         # ---- argument blocks: everything that never changes is filled once
         self.args = _native.RetrieveArgs()
         a = self.args
@@ -128,8 +132,8 @@ class _Step:
         if bank._p2p is not None and bank._p2p.world_size > 1:
             bank._p2p.fill_args(a)
         self.io = _native.HostIO()
-        self._q0_ptr = self.q0.data_ptr()
-        self._q1_ptr = 0 if self.q1 is None else self.q1.data_ptr()
+        self._q0_ptr = [t.data_ptr() for t in self.q0]
+        self._q1_ptr = [0 if t is None else t.data_ptr() for t in self.q1]
         self._view_cache: Dict[tuple, Dict[str, torch.Tensor]] = {}
         self._prompt_mode = -1            # which prompt tables the argument block currently points at
         self._tail_bound: Dict[bool, int] = {}
@@ -204,19 +208,22 @@ class _Step:
         dev = bank.device
         turn = self.turn
         self.turn ^= 1
+        if self.in_flight[turn]:             # the submitted step that last used this turn's buffers must be through
+            self.done_events[turn].synchronize()
+            self.in_flight[turn] = False
         self._bind_turn(turn)
         if not img.is_cuda:
             if not img.is_pinned():          # pageable host memory: stage through a pinned buffer of our own
-                if self.h_q is None:
-                    self.h_q = (torch.empty((self.b, self.d0), dtype=self.dtype).pin_memory(),
-                                torch.empty((self.b, self.d1), dtype=self.dtype).pin_memory() if self.d1 else None)
-                self.h_q[0].copy_(img)
-                img = self.h_q[0]
+                if self.h_q[turn] is None:
+                    self.h_q[turn] = (torch.empty((self.b, self.d0), dtype=self.dtype).pin_memory(),
+                                      torch.empty((self.b, self.d1), dtype=self.dtype).pin_memory() if self.d1 else None)
+                self.h_q[turn][0].copy_(img)
+                img = self.h_q[turn][0]
                 if txt is not None:
-                    self.h_q[1].copy_(txt)
-                    txt = self.h_q[1]
+                    self.h_q[turn][1].copy_(txt)
+                    txt = self.h_q[turn][1]
             io.h_q0, io.h_q1 = img.data_ptr(), (0 if txt is None else txt.data_ptr())
-            a.q0, a.q1 = self._q0_ptr, self._q1_ptr
+            a.q0, a.q1 = self._q0_ptr[turn], self._q1_ptr[turn]
         else:
             io.h_q0 = io.h_q1 = 0
             a.q0, a.q1 = img.data_ptr(), (0 if txt is None else txt.data_ptr())
@@ -270,11 +277,29 @@ class _Step:
         else:
             io.d_out = io.h_out = 0
             io.out_bytes, io.sync = 0, 0
+        copy_streams = bank._copy_streams() if to_host == "async" else None
+        if copy_streams is not None:
+            # Inputs on st_in, results on st_out.  The input copy overwrites this turn's device staging: the submitted
+            # step that last read it was awaited above (in_flight), a blocking call has returned, and a non-blocking
+            # call with host inputs left an event behind (stage_busy) that the input stream waits for.
+            if self.stage_busy[turn] is not None:
+                copy_streams[0].wait_event(self.stage_busy[turn])
+                self.stage_busy[turn] = None
+            io.stream_in, io.stream_out = copy_streams[0].cuda_stream, copy_streams[1].cuda_stream
+        else:
+            io.stream_in = io.stream_out = 0
         K.retrieve(a, dev, io)
+        if not to_host and (io.h_q0 or staged_prefix):
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(dev))
+            self.stage_busy[turn] = ev
         out: Dict[str, object] = {"device": self._cached_views(turn, stride, False), "stride": stride}
         if to_host == "async":
             ev = self.done_events[turn]
-            ev.record(torch.cuda.current_stream(dev))
+            ev.record(copy_streams[1])
+            self.in_flight[turn] = True
+            self.gen[turn] += 1
+            out["owner"] = (self, turn, self.gen[turn])
             if staged_prefix:
                 self.pre_done[turn] = ev
             out["done"] = ev
@@ -315,6 +340,9 @@ class PendingRetrieval:
             if ev is None:             # the NCCL-exchange path has already synchronised
                 return host
             ev.synchronize()
+            owner = self._step.get("owner")
+            if owner is not None and owner[0].gen[owner[1]] == owner[2]:
+                owner[0].in_flight[owner[1]] = False
             status = int(host["_status_np"][0])
             if status != 0:
                 raise K._native.NativeError(
@@ -362,6 +390,7 @@ class RetrievalBank:
         self._steps: Dict[tuple, _Step] = {}
         self._zero_seg: Optional[torch.Tensor] = None
         self._pool = None
+        self._copy_stream_pair = None
         self._prefetched: Dict[tuple, object] = {}
         self._prefetch_lock = threading.Lock()
         self.exchange = CandidateExchange(process_group if shard else None)
@@ -622,6 +651,14 @@ class RetrievalBank:
             tokens = tokens.to(self.device, non_blocking=True)
         txt = self.clip_model.encode_text(tokens)
         return img.detach().contiguous(), (None if txt is None else txt.detach().contiguous())
+
+    def _copy_streams(self):
+        """Input / result copy streams of the two-deep host pipeline (submit_prompt_ids_host): copies of the neighbouring
+        steps overlap the current step's kernel."""
+        if self._copy_stream_pair is None:
+            with torch.cuda.device(self.device):
+                self._copy_stream_pair = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))
+        return self._copy_stream_pair
 
     def _zero_seg_off(self) -> torch.Tensor:
         if self._zero_seg is None or self._zero_seg.numel() != 9 + len(self.answer_strings):

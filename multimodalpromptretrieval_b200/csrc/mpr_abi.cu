@@ -44,11 +44,14 @@ struct mpr_context {
     int cooperative = 1;                    // fused-tail launches are cooperative (MPR_NO_COOP=1: plain launch)
     int use_reg_list = 1;                   // k + skip <= 8: lists in registers (MPR_NO_REGLIST=1: shared memory)
     int first_wait_ns = 16000;              // first tile: bounded wait for the shared thresholds (MPR_FIRST_WAIT_NS; -1 = legacy start)
+    int q_coop = 1;                         // warp-cooperative coalesced q-tile fill (MPR_NO_QCOOP=1: a thread per row)
     int tail_floor = 1;                     // pool merge drops keys below the final shared threshold (MPR_NO_TAIL_FLOOR=1)
     unsigned long long xchg_timeout_ns = 60ull * 1000000000ull;
     // workspaces whose control words are known to be zero over `second` leading bytes (the library zeroed them when it
     // first saw the pointer, every launch leaves them zero); most recently used last, at most 16
     std::vector<std::pair<const void*, size_t>> clean_ws;
+    cudaEvent_t io_events[4] = {nullptr, nullptr, nullptr, nullptr};   // mpr_retrieve_host with copy streams
+    int io_turn = 0;
     int last_launches = 0;                  // kernel launches of the last mpr_retrieve
     int prof_used = -1;                     // -1 = profiling off
     int prof_last_n = 0;                    // launches recorded by the last begin/end pair
@@ -337,6 +340,11 @@ static int run_step(mpr_context* h, const mpr_retrieve_args& a, float* dump, cud
     p.gthr = (!kDump && h->shared_thr) ? reinterpret_cast<uint32_t*>(ws + wl.gthr_off) : nullptr;
     p.ns = wl.ns;
     p.fused_tail = fused_tail ? 1 : 0;
+    {
+        const ScanSmemLayout lay = scan_smem_layout(pl.n_chunks, pl.q_box_rows, pl.kk_pad, pl.cand_cap, pl.n_stages,
+                                                    pl.sub_per_stage, pl.n_epi_groups);
+        p.q_coop = (h->q_coop && pl.q_tmem && !(raw && a.normalise) && lay.bias_off - lay.list_off >= 8u * 4096u) ? 1 : 0;
+    }
     // waiting for the slots only pays when every slot is fed by some list that gets a tile right away
     p.first_wait_ns = (h->first_wait_ns > 0 && (pl.n_splits < wl.ns || pl.n_tiles < 2 * pl.n_splits * pl.n_epi_groups))
                           ? 0 : h->first_wait_ns;
@@ -513,6 +521,7 @@ int mpr_create(int device, mpr_handle_t* out) {
         if (flag("MPR_NO_COOP")) h->cooperative = 0;
         if (flag("MPR_NO_REGLIST")) h->use_reg_list = 0;
         if (flag("MPR_NO_TAIL_FLOOR")) h->tail_floor = 0;
+        if (flag("MPR_NO_QCOOP")) h->q_coop = 0;
         const char* fw = getenv("MPR_FIRST_WAIT_NS");
         if (fw) h->first_wait_ns = atoi(fw) < 0 ? -1 : (atoi(fw) > 100000 ? 100000 : atoi(fw));
         const char* dc = getenv("MPR_DEBUG_COUNTERS");
@@ -580,6 +589,7 @@ int mpr_destroy(mpr_handle_t h) {
     if (!h) return MPR_OK;
     DeviceGuard guard(h->device);
     for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->io_events) if (e) cudaEventDestroy(e);
     if (h->d_err) cudaFree(h->d_err);
     if (h->d_dbg) cudaFree(h->d_dbg);
     delete h;
@@ -693,14 +703,26 @@ int mpr_retrieve_host(mpr_handle_t h, const mpr_retrieve_args* a, const mpr_host
     if (a->b == 0) return MPR_OK;
     DeviceGuard guard(h->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    static const size_t kElem[3] = {4, 2, 2};
-    if (io->h_q0) {
+    cudaStream_t st_in = io->stream_in ? static_cast<cudaStream_t>(io->stream_in) : st;
+    cudaStream_t st_out = io->stream_out ? static_cast<cudaStream_t>(io->stream_out) : st;
+    if ((st_in != st || st_out != st) && !h->io_events[0]) {
+        for (int i = 0; i < 4; ++i) CUDA_TRY(h, cudaEventCreateWithFlags(&h->io_events[i], cudaEventDisableTiming));
+    }
+    // rotating pair of events: "inputs of this call are on the device" / "this call's step has run"
+    cudaEvent_t ev_in = h->io_events[2 * (h->io_turn & 1)], ev_step = h->io_events[2 * (h->io_turn & 1) + 1];
+    h->io_turn ^= 1;
+    bool copied_in = false;
+    {
+        cudaStream_t st = st_in;      // the copies below go to the input stream
+        static const size_t kElem[3] = {4, 2, 2};
+        if (io->h_q0) {
         if (!a->q0) return fail(h, MPR_EINVAL, "h_q0 given but a->q0 (device staging) is null");
         CUDA_TRY(h, cudaMemcpyAsync(const_cast<void*>(a->q0), io->h_q0, static_cast<size_t>(a->b) * a->d0 * kElem[a->q_dtype],
                                     cudaMemcpyHostToDevice, st));
         if (io->h_q1 && a->q1)
             CUDA_TRY(h, cudaMemcpyAsync(const_cast<void*>(a->q1), io->h_q1, static_cast<size_t>(a->b) * a->d1 * kElem[a->q_dtype],
                                         cudaMemcpyHostToDevice, st));
+        copied_in = true;
     }
     if (io->h_prefix_ids && a->answer_id) {
         if (!io->h_prefix_off) return fail(h, MPR_EINVAL, "h_prefix_off is null");
@@ -709,12 +731,23 @@ int mpr_retrieve_host(mpr_handle_t h, const mpr_retrieve_args* a, const mpr_host
                                         sizeof(int32_t) * static_cast<size_t>(io->n_prefix_ids), cudaMemcpyHostToDevice, st));
         CUDA_TRY(h, cudaMemcpyAsync(const_cast<int32_t*>(a->prefix_off), io->h_prefix_off,
                                     sizeof(int32_t) * (static_cast<size_t>(a->b) + 1), cudaMemcpyHostToDevice, st));
+        copied_in = true;
+    }
+    }
+    if (st_in != st && copied_in) {
+        CUDA_TRY(h, cudaEventRecord(ev_in, st_in));
+        CUDA_TRY(h, cudaStreamWaitEvent(st, ev_in, 0));
     }
     rc = run_step<false>(h, *a, nullptr, st);
     if (rc) return rc;
-    if (io->h_out && io->d_out && io->out_bytes)
-        CUDA_TRY(h, cudaMemcpyAsync(io->h_out, io->d_out, io->out_bytes, cudaMemcpyDeviceToHost, st));
-    if (io->sync) CUDA_TRY(h, cudaStreamSynchronize(st));
+    if (io->h_out && io->d_out && io->out_bytes) {
+        if (st_out != st) {
+            CUDA_TRY(h, cudaEventRecord(ev_step, st));
+            CUDA_TRY(h, cudaStreamWaitEvent(st_out, ev_step, 0));
+        }
+        CUDA_TRY(h, cudaMemcpyAsync(io->h_out, io->d_out, io->out_bytes, cudaMemcpyDeviceToHost, st_out));
+    }
+    if (io->sync) CUDA_TRY(h, cudaStreamSynchronize(st_out));
     return MPR_OK;
 }
 

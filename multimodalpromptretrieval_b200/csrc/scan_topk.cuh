@@ -31,6 +31,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <math_constants.h>
+#include <type_traits>
 
 #include "bank_build.cuh"
 #include "ptx.cuh"
@@ -88,6 +89,8 @@ struct ScanParams {
                            // that the 32 lanes (= 32 queries) of a warp touch 4 sectors per slot, not 32
     int ns;                // threshold slots per query (multiple of 4, >= kk)
     int fused_tail;        // 1: grid barrier + tail.cuh in this launch (grid must be co-resident)
+    int q_coop;            // TMEM q-tile filled warp-cooperatively: coalesced loads -> swizzled scratch in the (not yet used)
+                           // list memory -> each thread's row -> tcgen05.st (needs >= 32 KiB of list memory, no normalise)
     int first_wait_ns;     // first tile of a list: how long to wait for every threshold slot of the query to be filled
                            // after the tile's maximum was published (0: a single look; < 0: legacy blind-chunk start)
     unsigned long long* dbg;  // debug counters (MPR_DEBUG_COUNTERS=1) or nullptr: [0] candidates admitted, [1] warp flushes,
@@ -428,7 +431,8 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         uint64_t* my_list = lists + static_cast<size_t>(grp * kUmmaM + row) * scan_row_stride(kk_pad, p.cand_cap);   // [0, kk)
         uint2* my_pend = reinterpret_cast<uint2*>(my_list + kk_pad);                      // (score bits, row)
         const bool active_group = grp < p.n_epi_groups;      // an idle group owns no list memory
-        if (!kRegList && active_group) for (int i = 0; i < kk; ++i) my_list[i] = 0ull;
+        // (with q_coop the list memory first serves as the q-tile fill's scratch; the lists are zeroed after it)
+        if (!kRegList && active_group && !(kQTmem && p.q_coop)) for (int i = 0; i < kk; ++i) my_list[i] = 0ull;
         // thr = max(private threshold: score of this list's kk-th best, shared threshold: just below the minimum over
         // the query's ns published slot maxima).  `>` is exact for both: rows arrive in ascending order, so a later row
         // displaces the kk-th best only with a STRICTLY higher score; and ns distinct rows are known to score at least
@@ -516,7 +520,104 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             // epilogue groups split the row's 64-element chunks between them (both can reach every lane quadrant).
             const uint32_t q_taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
             const size_t qrow_idx = static_cast<size_t>(valid ? q0 + row : 0);
-            if constexpr (kFuseQ) {
+            if (p.q_coop) {
+                // Warp-cooperative fill.  A thread pulling its own row reads 16 bytes per request from 32 different lines
+                // (half of every sector fetched is wasted, and 148 CTAs pull the same 256 KB through L2 at once); here the
+                // 32 rows x 64 elements of a chunk are read fully coalesced (8 lanes per row), rounded to bf16 and
+                // transposed through 4 KiB of swizzled scratch so that each thread ends up with its own row's 128 bytes.
+                // The sum of squares is taken by the owning thread over the rounded values in the same order as the
+                // per-thread path, so q_bias_out is bit-identical.
+                uint8_t* scr = smem + lay.list_off + (warp - 2) * 4096;
+                const void* s0 = kFuseQ ? p.qsrc0 : static_cast<const void*>(p.q);
+                const void* s1 = kFuseQ ? p.qsrc1 : nullptr;
+                const int sd0 = kFuseQ ? p.qd0 : p.d, sd1 = kFuseQ ? p.qd1 : 0;
+                const int sdt = kFuseQ ? p.q_dtype : static_cast<int>(kSrcBF16);
+                float rs = 0.f;
+                // all 8 (16 for fp32) 128-bit loads of a chunk are issued before the first conversion: kWide is a
+                // compile-time constant so that the load loop has no branch the scheduler would not hoist loads across
+                auto fill_chunk = [&](auto wide_tag, int c) {
+                    constexpr bool kWide = decltype(wide_tag)::value;        // fp32 source: two 128-bit loads per unit
+                    uint4 raw[8][kWide ? 2 : 1];
+                    bool ok[8];
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int unit_idx = it * 32 + lane;
+                        const int rl = unit_idx >> 3, u = unit_idx & 7;
+                        ok[it] = quad * 32 + rl < q_valid;
+                        const size_t grow = static_cast<size_t>(q0 + (ok[it] ? quad * 32 + rl : 0));
+                        const int col = c * kChunkK + u * 8;
+                        const bool first = col < sd0;
+                        const size_t off = first ? grow * sd0 + col : grow * sd1 + (col - sd0);
+                        const uint4* src = reinterpret_cast<const uint4*>(
+                            static_cast<const uint8_t*>(first ? s0 : s1) + off * (kWide ? 4 : 2));
+                        raw[it][0] = __ldg(src);
+                        if constexpr (kWide) raw[it][1] = __ldg(src + 1);
+                    }
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int unit_idx = it * 32 + lane;
+                        const int rl = unit_idx >> 3, u = unit_idx & 7;
+                        uint32_t pk[4];
+                        if constexpr (kWide) {
+                            const uint32_t f[8] = {raw[it][0].x, raw[it][0].y, raw[it][0].z, raw[it][0].w,
+                                                   raw[it][1].x, raw[it][1].y, raw[it][1].z, raw[it][1].w};
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const __nv_bfloat16 lo = __float2bfloat16_rn(__uint_as_float(f[2 * i]));
+                                const __nv_bfloat16 hi = __float2bfloat16_rn(__uint_as_float(f[2 * i + 1]));
+                                pk[i] = static_cast<uint32_t>(__bfloat16_as_ushort(lo)) |
+                                        (static_cast<uint32_t>(__bfloat16_as_ushort(hi)) << 16);
+                            }
+                        } else {
+                            const uint32_t h[4] = {raw[it][0].x, raw[it][0].y, raw[it][0].z, raw[it][0].w};
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                if (sdt == kSrcF16) {
+                                    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h[i]));
+                                    pk[i] = static_cast<uint32_t>(__bfloat16_as_ushort(__float2bfloat16_rn(f.x))) |
+                                            (static_cast<uint32_t>(__bfloat16_as_ushort(__float2bfloat16_rn(f.y))) << 16);
+                                } else {
+                                    pk[i] = h[i];                            // bf16 rows pass through
+                                }
+                            }
+                        }
+                        const uint4 out = ok[it] ? make_uint4(pk[0], pk[1], pk[2], pk[3]) : make_uint4(0u, 0u, 0u, 0u);
+                        *reinterpret_cast<uint4*>(scr + rl * 128 + ((u ^ (rl & 7)) << 4)) = out;
+                    }
+                };
+                for (int c = grp; c < p.n_chunks; c += kEpiGroups) {
+                    if (sdt == kSrcF32) fill_chunk(std::true_type{}, c);
+                    else                fill_chunk(std::false_type{}, c);
+                    __syncwarp();
+                    uint32_t w[32];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const uint4 t = *reinterpret_cast<const uint4*>(scr + lane * 128 + ((u ^ (lane & 7)) << 4));
+                        w[4 * u + 0] = t.x; w[4 * u + 1] = t.y; w[4 * u + 2] = t.z; w[4 * u + 3] = t.w;
+                    }
+                    if constexpr (kFuseQ) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const float flo = __uint_as_float(w[i] << 16), fhi = __uint_as_float(w[i] & 0xFFFF0000u);
+                            rs = fmaf(flo, flo, rs);
+                            rs = fmaf(fhi, fhi, rs);
+                        }
+                    }
+                    ptx::tmem_st_32x32b_x32(q_taddr + c * (kChunkK / 2), w);
+                    __syncwarp();      // the scratch is rewritten by the next chunk
+                }
+                if constexpr (kFuseQ) {
+                    if (split == 0 && p.q_bias_out) {                   // -0.5*|q|^2 for return_dists: the two halves meet here
+                        scratch[grp * kUmmaM + row] = rs;
+                        ptx::named_bar_sync(3, 256);
+                        if (grp == 0 && valid) p.q_bias_out[q0 + row] = -0.5f * (rs + scratch[kUmmaM + row]);
+                    }
+                }
+                if constexpr (!kRegList) {
+                    ptx::named_bar_sync(4, 256);       // every warp is through with its scratch: the memory becomes lists
+                    if (active_group) for (int i = 0; i < kk; ++i) my_list[i] = 0ull;
+                }
+            } else if constexpr (kFuseQ) {
                 auto load_q8 = [&](int col, float (&x)[8]) {      // 8 consecutive elements of [src0 | src1]
                     if (col < p.qd0) load8(p.qsrc0, p.q_dtype, qrow_idx * p.qd0 + col, x);
                     else             load8(p.qsrc1, p.q_dtype, qrow_idx * p.qd1 + (col - p.qd0), x);
