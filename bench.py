@@ -534,6 +534,18 @@ def run_native(args):
     else:
         ranks_agree = True
 
+    if os.environ.get("MPR_DEBUG_COUNTERS") and rank == 0:
+        # tuning aid: per-CTA timeline of one more device step (see tools/probe_one.py for the event names)
+        device_step()
+        torch.cuda.synchronize()
+        tl = K.debug_timeline(K.search_plan(b, n_local, d, kk, dev.index)["n_ctas"], dev.index) / 1e3
+        names = {1: "q_ready", 2: "producer_done", 7: "cta_done", 8: "past_grid_barrier", 9: "tail_done", 15: "tile0_ready",
+                 16: "t0_bound_ready", 20: "t0_released", 23: "t0_published"}
+        for k_, nm in names.items():
+            col = tl[:, k_]
+            col = col[col >= 0]
+            if col.size:
+                sys.stderr.write(f"timeline {nm:18s} min {col.min():8.1f} p50 {np.median(col):8.1f} max {col.max():8.1f} us\n")
     if rank == 0:
         h2d = q_host.numel() * 4 + int(pre_ids.numel() + pre_off.numel()) * 4
         d2h = int(bank._steps[next(iter(bank._steps))].head_bytes) + int(out0["stride"]) * b * 16

@@ -44,6 +44,7 @@ struct mpr_context {
     int cooperative = 1;                    // fused-tail launches are cooperative (MPR_NO_COOP=1: plain launch)
     int use_reg_list = 1;                   // k + skip <= 8: lists in registers (MPR_NO_REGLIST=1: shared memory)
     int first_wait_ns = 16000;              // first tile: bounded wait for the shared thresholds (MPR_FIRST_WAIT_NS; -1 = legacy start)
+    int thr_rep_log2 = 2;                   // up to 4 replica words per threshold slot (MPR_THR_REPLICAS=1|2|4)
     int q_coop = 1;                         // warp-cooperative coalesced q-tile fill (MPR_NO_QCOOP=1: a thread per row)
     int tail_floor = 1;                     // pool merge drops keys below the final shared threshold (MPR_NO_TAIL_FLOOR=1)
     unsigned long long xchg_timeout_ns = 60ull * 1000000000ull;
@@ -188,15 +189,18 @@ static int make_plan(mpr_context* h, int b, int64_t n_local, int d, int kk, Scan
 // Workspace = [control block | tile counters | shared thresholds] (all-zero between launches) + partial lists.
 struct WsLayout {
     size_t tile_ctr_off, gthr_off, zero_bytes, part_off, total;
-    int ns;
+    int ns, rep_log2;
 };
 
-static WsLayout ws_layout(const ScanPlan& pl, int b, int kk) {
+static WsLayout ws_layout(const mpr_context* h, const ScanPlan& pl, int b, int kk) {
     WsLayout w;
     w.ns = (kk + 3) & ~3;
+    w.rep_log2 = 0;
+    const int max_words = pl.reg_list ? 16 : 32;       // what the scan variant holds in registers (kThrN)
+    while (w.rep_log2 < h->thr_rep_log2 && (w.ns << (w.rep_log2 + 1)) <= max_words) ++w.rep_log2;
     w.tile_ctr_off = 16;
     w.gthr_off = round16(w.tile_ctr_off + sizeof(uint32_t) * static_cast<size_t>(pl.n_qtiles));
-    w.zero_bytes = w.gthr_off + sizeof(uint32_t) * static_cast<size_t>(b) * w.ns;
+    w.zero_bytes = w.gthr_off + sizeof(uint32_t) * static_cast<size_t>(b) * (w.ns << w.rep_log2);
     w.part_off = round16(w.zero_bytes);
     w.total = w.part_off + static_cast<size_t>(pl.n_splits) * kEpiGroups * b * kk * sizeof(uint64_t);
     return w;
@@ -254,7 +258,7 @@ static int run_step(mpr_context* h, const mpr_retrieve_args& a, float* dump, cud
     int rc = make_plan(h, b, a.n_local, d, kk, &pl);
     h->use_reg_list = saved_reg;
     if (rc) return rc;
-    const WsLayout wl = ws_layout(pl, b, kk);
+    const WsLayout wl = ws_layout(h, pl, b, kk);
     if (a.workspace_bytes < wl.total)
         return fail(h, MPR_EWORKSPACE, "workspace too small: %zu < %zu", a.workspace_bytes, wl.total);
     h->last_launches = 0;
@@ -339,6 +343,7 @@ static int run_step(mpr_context* h, const mpr_retrieve_args& a, float* dump, cud
     p.tile_ctr = (!kDump && !pair && h->dynamic_tiles) ? reinterpret_cast<uint32_t*>(ws + wl.tile_ctr_off) : nullptr;
     p.gthr = (!kDump && h->shared_thr) ? reinterpret_cast<uint32_t*>(ws + wl.gthr_off) : nullptr;
     p.ns = wl.ns;
+    p.thr_rep_log2 = wl.rep_log2;
     p.fused_tail = fused_tail ? 1 : 0;
     {
         const ScanSmemLayout lay = scan_smem_layout(pl.n_chunks, pl.q_box_rows, pl.kk_pad, pl.cand_cap, pl.n_stages,
@@ -364,6 +369,7 @@ static int run_step(mpr_context* h, const mpr_retrieve_args& a, float* dump, cud
     t.n_tile_ctr = pl.n_qtiles;
     t.gthr = p.gthr;
     t.ns = wl.ns;
+    t.thr_rep_log2 = wl.rep_log2;
     t.use_floor = h->tail_floor;
     t.out_keys = a.out_keys;
     t.out_score = a.out_score;
@@ -522,6 +528,8 @@ int mpr_create(int device, mpr_handle_t* out) {
         if (flag("MPR_NO_REGLIST")) h->use_reg_list = 0;
         if (flag("MPR_NO_TAIL_FLOOR")) h->tail_floor = 0;
         if (flag("MPR_NO_QCOOP")) h->q_coop = 0;
+        const char* tr = getenv("MPR_THR_REPLICAS");
+        if (tr) h->thr_rep_log2 = tr[0] == '1' ? 0 : tr[0] == '2' ? 1 : 2;
         const char* fw = getenv("MPR_FIRST_WAIT_NS");
         if (fw) h->first_wait_ns = atoi(fw) < 0 ? -1 : (atoi(fw) > 100000 ? 100000 : atoi(fw));
         const char* dc = getenv("MPR_DEBUG_COUNTERS");
@@ -653,7 +661,7 @@ size_t mpr_search_workspace_bytes(mpr_handle_t h, int b, int64_t n_local, int d,
     if (!h) return 0;
     ScanPlan pl;
     if (make_plan(h, b, n_local, d, kk, &pl)) return 0;
-    return ws_layout(pl, b, kk).total;
+    return ws_layout(h, pl, b, kk).total;
 }
 
 int mpr_search_plan(mpr_handle_t h, int b, int64_t n_local, int d, int kk, int* n_ctas, int* n_splits, int* n_qtiles,

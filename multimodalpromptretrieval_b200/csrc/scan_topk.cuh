@@ -56,6 +56,7 @@ constexpr int kEpiGroups = 2;                 // epilogue groups; group g owns t
 constexpr int kCandCapMax = 16;               // per-query pending-candidate slots (a flush leaves >= 8 free)
 constexpr int kTileRing = 64;                 // scheduler -> consumers tile-id ring (entries); >= the producer's lead
 constexpr uint32_t kTileEnd = 0xFFFFFFFFu;
+constexpr int kMaxQChunkBars = 8;             // per-K-chunk "q-tile chunk is in tensor memory" barriers (D <= 512)
 
 struct ScanParams {
     int b_total;       // queries in the batch
@@ -88,6 +89,9 @@ struct ScanParams {
     uint32_t* gthr;        // [ns][b_total] shared admission thresholds, ordered-u32 scores (nullptr: off); slot-major so
                            // that the 32 lanes (= 32 queries) of a warp touch 4 sectors per slot, not 32
     int ns;                // threshold slots per query (multiple of 4, >= kk)
+    int thr_rep_log2;      // every slot is kept as 2^r replicas (word slot * R + replica; a list feeds one of them, a reader
+                           // takes the maximum): the first publish of ~300 lists lands at the same instant, and with one
+                           // word per slot each 128-byte line took ~37 atomic requests in a row.  ns << r <= 32
     int fused_tail;        // 1: grid barrier + tail.cuh in this launch (grid must be co-resident)
     int q_coop;            // TMEM q-tile filled warp-cooperatively: coalesced loads -> swizzled scratch in the (not yet used)
                            // list memory -> each thread's row -> tcgen05.st (needs >= 32 KiB of list memory, no normalise)
@@ -120,7 +124,7 @@ __host__ __device__ inline ScanSmemLayout scan_smem_layout(int n_chunks, int q_b
     l.ring_off = l.bias_off + kAccBufs * kTileRows * 4u;
     l.scr_off = l.ring_off + kTileRing * 8u;
     l.bar_off = l.scr_off + 2 * kUmmaM * 4u;
-    l.total = l.bar_off + (1 + 2 * kMaxStages + 2 * kAccBufs) * 8u + 16u;
+    l.total = l.bar_off + (1 + 2 * kMaxStages + 2 * kAccBufs + kMaxQChunkBars) * 8u + 16u;
     return l;
 }
 
@@ -211,8 +215,9 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     auto bar_empty = [&](int s) { return bar_base + 8u + 8u * (kMaxStages + s); };
     auto bar_tfull = [&](int b) { return bar_base + 8u + 8u * (2 * kMaxStages + b); };
     auto bar_tempty = [&](int b) { return bar_base + 8u + 8u * (2 * kMaxStages + kAccBufs + b); };
+    auto bar_qc = [&](int c) { return bar_base + 8u + 8u * (2 * kMaxStages + 2 * kAccBufs + c); };
     volatile uint32_t* tmem_slot =
-        reinterpret_cast<volatile uint32_t*>(smem + lay.bar_off + (1 + 2 * kMaxStages + 2 * kAccBufs) * 8u);
+        reinterpret_cast<volatile uint32_t*>(smem + lay.bar_off + (1 + 2 * kMaxStages + 2 * kAccBufs + kMaxQChunkBars) * 8u);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -241,6 +246,8 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             ptx::mbar_init(bar_tfull(b), 1);
             ptx::mbar_init(bar_tempty(b), 4);   // one arrive per epilogue warp
         }
+        if constexpr (kQTmem)
+            for (int c = 0; c < kMaxQChunkBars; ++c) ptx::mbar_init(bar_qc(c), 4);   // the four warps of the chunk's group
         ptx::fence_mbar_init();
         if constexpr (!kWarpsFillQ) ptx::prefetch_tensormap(&tmap_q);
         if (p.n_tiles > 0) ptx::prefetch_tensormap(&tmap_bank);
@@ -367,9 +374,13 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         const uint32_t b_lo0 = (stage_smem >> 4) & 0x3FFFu;
         const uint32_t a_lo0 = (q_smem >> 4) & 0x3FFFu;
         const uint32_t slab_lo = static_cast<uint32_t>(p.q_box_rows) * 8u;      // slab bytes >> 4
-        ptx::mbar_wait(bar_q, 0, p.err, kErrQFull);
-        ptx::tc_fence_after();
-        if (lane == 0) stamp(1);
+        // with the cooperative fill the q-tile arrives chunk by chunk and the first tile's MMAs follow it chunk by chunk
+        const bool q_by_chunk = kQTmem && p.q_coop;
+        if (!q_by_chunk) {
+            ptx::mbar_wait(bar_q, 0, p.err, kErrQFull);
+            ptx::tc_fence_after();
+            if (lane == 0) stamp(1);
+        }
         const int spp = p.sub_per_stage;
         int s = 0;
         uint32_t ph = 0;
@@ -385,6 +396,12 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             for (int j0 = 0; j0 < p.n_chunks; j0 += spp) {
                 const int ns = min(spp, p.n_chunks - j0);
                 if (j0 > 0) ptx::mbar_wait(bar_full(s), ph, p.err, kErrFull);
+                if constexpr (kQTmem) {
+                    if (q_by_chunk && lt == 0) {
+                        for (int u = 0; u < ns; ++u) ptx::mbar_wait(bar_qc(j0 + u), 0, p.err, kErrQFull);
+                        if (j0 + ns == p.n_chunks && lane == 0) stamp(1);
+                    }
+                }
                 ptx::tc_fence_after();
                 if (ptx::elect_one()) {
 #pragma unroll
@@ -604,7 +621,10 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                         }
                     }
                     ptx::tmem_st_32x32b_x32(q_taddr + c * (kChunkK / 2), w);
+                    ptx::tmem_wait_st();
+                    ptx::tc_fence_before();
                     __syncwarp();      // the scratch is rewritten by the next chunk
+                    if (lane == 0) ptx::mbar_arrive(bar_qc(c));
                 }
                 if constexpr (kFuseQ) {
                     if (split == 0 && p.q_bias_out) {                   // -0.5*|q|^2 for return_dists: the two halves meet here
@@ -700,7 +720,8 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         // shared threshold: minimum over this query's ns slots (0 = some slot still empty -> no bound yet)
         // slot of this list: group 1 is offset by ns/2, so that the group-0 lists ALONE feed every slot — group 0 owns a
         // CTA's first tile, and its first-tile wait below must not depend on second tiles (one tile time later)
-        const int my_slot_ = p.gthr ? (split + grp * (p.ns >> 1)) % p.ns : 0;
+        const int my_slot_ = p.gthr ? (((split + grp * (p.ns >> 1)) % p.ns) << p.thr_rep_log2) +
+                                          ((split / p.ns) & ((1 << p.thr_rep_log2) - 1)) : 0;      // word index: slot * R + replica
         const uint32_t* my_gthr = p.gthr ? p.gthr + (valid ? q0 + row : q0) : nullptr;     // slot i at my_gthr[i * b_total]
         const size_t thr_pitch = static_cast<size_t>(p.b_total);
         auto apply_shared = [&](uint32_t m) {
@@ -711,28 +732,46 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 if (p.dbg && valid) atomicAdd(p.dbg + 5, 1ull);
             }
         };
-        auto slots_min = [&]() -> uint32_t {        // one loaded-L2 round trip (1-2 us under a full scan)
+        const int thr_words = p.ns << p.thr_rep_log2;
+        constexpr int kThrN = kRegList ? 16 : 32;       // words held in registers (the host keeps ns << r within it)
+        // kThrN words (static indices; word i = slot (i >> r), replica (i & (R-1))) -> minimum over the slots of the maximum
+        // over each slot's replicas.  Unused words must be 0xFFFFFFFF... for the min and are never the max of a slot.
+        auto fold_words = [&](uint32_t (&v)[kThrN]) -> uint32_t {
+            if (p.thr_rep_log2 >= 1) {
+#pragma unroll
+                for (int i = 0; i < kThrN; i += 2) v[i] = max(v[i], v[i + 1]);
+            }
+            if (p.thr_rep_log2 >= 2) {
+#pragma unroll
+                for (int i = 0; i < kThrN; i += 4) v[i] = max(v[i], v[i + 2]);
+            }
+            const int step = 1 << p.thr_rep_log2;
             uint32_t m = 0xFFFFFFFFu;
-#pragma unroll 4
-            for (int i = 0; i < p.ns; ++i) m = min(m, __ldcg(my_gthr + i * thr_pitch));
+#pragma unroll
+            for (int i = 0; i < kThrN; ++i)
+                if ((i & (step - 1)) == 0 && i < thr_words) m = min(m, v[i]);
             return m;
+        };
+        auto load_words = [&](uint32_t (&v)[kThrN]) {
+#pragma unroll
+            for (int i = 0; i < kThrN; ++i) v[i] = i < thr_words ? __ldcg(my_gthr + i * thr_pitch) : 0u;
+        };
+        auto slots_min = [&]() -> uint32_t {        // one loaded-L2 round trip (1-2 us under a full scan)
+            uint32_t v[kThrN];
+            load_words(v);
+            return fold_words(v);
         };
         auto refresh_shared = [&]() { apply_shared(slots_min()); };      // blocking form
         // split form: the loads are issued when a tile starts and consumed when it ends, so their latency hides under the
         // tile's own work (a blocking refresh per tile cost ~2 us each during the ramp-up, ~15 us per launch)
-        constexpr int kThrN = kRegList ? 8 : 32;   // ns <= 8 for k + skip <= 8, <= 32 in general
         uint32_t thr_pre[kThrN];
         bool thr_pending = false;
         auto refresh_issue = [&]() {
-#pragma unroll
-            for (int i = 0; i < kThrN; ++i) thr_pre[i] = i < p.ns ? __ldcg(my_gthr + i * thr_pitch) : 0xFFFFFFFFu;
+            load_words(thr_pre);
             thr_pending = true;
         };
         auto refresh_consume = [&]() {
-            uint32_t m = 0xFFFFFFFFu;
-#pragma unroll
-            for (int i = 0; i < kThrN; ++i) m = min(m, thr_pre[i]);
-            apply_shared(m);
+            apply_shared(fold_words(thr_pre));
             thr_pending = false;
         };
         // publish this list's best score: the minimum over a query's slots bounds its global kk-th best from below

@@ -394,8 +394,9 @@ struct TailParams {
     uint32_t* ctrl;              // -> arrived, done
     uint32_t* tile_ctr;
     int n_tile_ctr;
-    uint32_t* gthr;              // [ns][b]
+    uint32_t* gthr;              // [ns * R][b]
     int ns;
+    int thr_rep_log2;            // 2^r replica words per slot (see ScanParams)
     int use_floor;               // pool merge: keys below the scan's final shared threshold are dropped unseen
     uint64_t* out_keys;          // [b][kk] (each may be nullptr)
     float* out_score;
@@ -421,7 +422,11 @@ __device__ __forceinline__ void block_tail_query(const TailParams& t, int q, uin
     // minimum, so a key whose score is strictly below it cannot be among the query's top kk (ties stay in).
     uint64_t floor0 = 0ull;
     if (t.gthr && t.use_floor) {
-        uint32_t mn = lane < t.ns ? __ldcg(t.gthr + static_cast<size_t>(lane) * t.b + q) : 0xFFFFFFFFu;
+        const int words = t.ns << t.thr_rep_log2;          // word = slot * R + replica, <= 32
+        uint32_t mn = lane < words ? __ldcg(t.gthr + static_cast<size_t>(lane) * t.b + q) : 0u;
+        if (t.thr_rep_log2 >= 1) mn = max(mn, __shfl_xor_sync(kFullMask, mn, 1));      // maximum over a slot's replicas
+        if (t.thr_rep_log2 >= 2) mn = max(mn, __shfl_xor_sync(kFullMask, mn, 2));
+        if (lane >= words) mn = 0xFFFFFFFFu;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mn = min(mn, __shfl_xor_sync(kFullMask, mn, o));
         if (mn > 0x00800000u) floor0 = (static_cast<uint64_t>(mn) << 32) - 1ull;
@@ -431,7 +436,7 @@ __device__ __forceinline__ void block_tail_query(const TailParams& t, int q, uin
     __syncthreads();
     if (warp == 0) {
         uint64_t elem = warp_merge_lists<false>(sbuf, kWarps, 32ll, 1ll, t.kk, lane);
-        if (t.gthr && lane < t.ns) t.gthr[static_cast<size_t>(lane) * t.b + q] = 0u;     // leave the thresholds zeroed
+        if (t.gthr && lane < (t.ns << t.thr_rep_log2)) t.gthr[static_cast<size_t>(lane) * t.b + q] = 0u;     // leave the thresholds zeroed
         if (t.xchg.world > 1) elem = warp_exchange(t.xchg, e, elem, q, t.kk, lane, t.status);
         store_merged(elem, q, t.kk, lane, t.out_keys, t.out_score, t.out_idx);
         if (t.prompt.answer_id) {
