@@ -534,10 +534,12 @@ def run_native(args):
     else:
         ranks_agree = True
 
-    if os.environ.get("MPR_DEBUG_COUNTERS") and rank == 0:
-        # tuning aid: per-CTA timeline of one more device step (see tools/probe_one.py for the event names)
+    if os.environ.get("MPR_DEBUG_COUNTERS"):
+        # tuning aid: per-CTA timeline of one more device step (see tools/probe_one.py for the event names); a sharded
+        # step is a collective, so every rank takes it and rank 0 reports
         device_step()
-        torch.cuda.synchronize()
+        barrier()
+    if os.environ.get("MPR_DEBUG_COUNTERS") and rank == 0:
         tl = K.debug_timeline(K.search_plan(b, n_local, d, kk, dev.index)["n_ctas"], dev.index) / 1e3
         names = {1: "q_ready", 2: "producer_done", 7: "cta_done", 8: "past_grid_barrier", 9: "tail_done", 15: "tile0_ready",
                  16: "t0_bound_ready", 20: "t0_released", 23: "t0_published"}

@@ -112,9 +112,9 @@ int mpr_merge_topk(mpr_handle_t h, const uint64_t* in_keys, int n_lists, int b, 
  * Candidate exchange over NVLink peer memory (one NVSwitch box).  Every rank allocates one buffer of
  * mpr_exchange_bytes(world, cap) bytes that is mapped into all peers (symmetric memory), zero-filled before first use;
  * cap >= b*kk of any search that will use it.  The exchange itself runs inside mpr_retrieve (see there): per query, the
- * rank's merged local top-kk is stored into every peer's buffer (plain P2P stores + a release flag), the peers'
- * deliveries of the same query are awaited and the `world` lists merged in rank order.  New in the build: the reference
- * is single-device (main.py:58-61).
+ * rank's merged local top-kk is stored into every peer's buffer as self-validating 8-byte words {half a key | epoch tag}
+ * (plain P2P stores, no fence and no flag), the peers' words of the same query are polled in the rank's own buffer and
+ * the `world` lists merged.  New in the build: the reference is single-device (main.py:58-61).
  */
 size_t mpr_exchange_bytes(int world, int cap);
 
@@ -259,6 +259,10 @@ int mpr_debug_counters(mpr_handle_t h, uint64_t* out8);
  * 8 past the grid barrier, 9 tail done, 10 second tile's data arrived, 11/12 first and 13/14 fourth tile consumed,
  * 15 first tile's accumulator ready, 16-19 its four 32-row chunks done, 20 its buffer released, 21 second tile's bias staged). */
 int mpr_debug_timeline(mpr_handle_t h, uint64_t* out, int n_ctas);
+/* With the same switch: for each of the last 64 scan launches (entry = launch number mod 64) out128[2e] = 2^63 - globaltimer
+ * of its first CTA's first instruction, out128[2e+1] = globaltimer of its last CTA's last instruction; *next_seq = number
+ * of launches so far.  Clears the ring.  Shows the gap between back-to-back launches. */
+int mpr_debug_launch_ring(mpr_handle_t h, uint64_t* out128, unsigned* next_seq);
 
 /* Kernel launches issued by the last mpr_retrieve / mpr_retrieve_host on this handle (bench bookkeeping). */
 int mpr_last_launch_count(mpr_handle_t h);

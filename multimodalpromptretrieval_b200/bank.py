@@ -383,7 +383,7 @@ class RetrievalBank:
         self.precomputed_features = bool(precomputed_features)
         self.exchange_capacity = int(exchange_capacity)
         if exchange not in ("nccl", "p2p"):
-            raise ValueError("exchange must be 'nccl' (all-gather + merge) or 'p2p' (peer-memory push + flag wait)")
+            raise ValueError("exchange must be 'nccl' (all-gather + merge) or 'p2p' (peer-memory push of epoch-tagged words inside the retrieval kernel)")
         self.exchange_mode = exchange
         self._p2p: Optional[P2PExchange] = None
         self._process_group = process_group if shard else None

@@ -45,6 +45,7 @@ struct mpr_context {
     int use_reg_list = 1;                   // k + skip <= 8: lists in registers (MPR_NO_REGLIST=1: shared memory)
     int first_wait_ns = 16000;              // first tile: bounded wait for the shared thresholds (MPR_FIRST_WAIT_NS; -1 = legacy start)
     int thr_rep_log2 = 2;                   // up to 4 replica words per threshold slot (MPR_THR_REPLICAS=1|2|4)
+    int pdl = 0;                            // programmatic dependent launch of the scan kernel (MPR_PDL=1)
     int q_coop = 1;                         // warp-cooperative coalesced q-tile fill (MPR_NO_QCOOP=1: a thread per row)
     int tail_floor = 1;                     // pool merge drops keys below the final shared threshold (MPR_NO_TAIL_FLOOR=1)
     unsigned long long xchg_timeout_ns = 60ull * 1000000000ull;
@@ -53,13 +54,15 @@ struct mpr_context {
     std::vector<std::pair<const void*, size_t>> clean_ws;
     cudaEvent_t io_events[4] = {nullptr, nullptr, nullptr, nullptr};   // mpr_retrieve_host with copy streams
     int io_turn = 0;
+    unsigned launch_seq = 0;                // scan launches so far (debug ring index)
     int last_launches = 0;                  // kernel launches of the last mpr_retrieve
     int prof_used = -1;                     // -1 = profiling off
     int prof_last_n = 0;                    // launches recorded by the last begin/end pair
     char err[512] = {0};
 };
 
-constexpr int kDbgWords = 8 + 24 * 2048;   // event counters + a 24-slot timeline for up to 2048 CTAs
+constexpr int kDbgRingOff = 8 + 24 * 2048;  // event counters + a 24-slot timeline for up to 2048 CTAs, then
+constexpr int kDbgWords = kDbgRingOff + 128; // a ring of [first entry, last exit] for the last 64 launches
 
 static thread_local char g_err[512] = "";
 
@@ -223,13 +226,14 @@ static int encode_2d(mpr_context* h, CUtensorMap* map, const void* ptr, uint64_t
 
 template <typename Kern>
 static cudaError_t launch_kernel(Kern kern, dim3 grid, uint32_t smem, cudaStream_t st, int cluster, bool cooperative,
-                                 const CUtensorMap& tq, const CUtensorMap& tb, const ScanParams& p, const TailParams& t) {
+                                 bool pdl, const CUtensorMap& tq, const CUtensorMap& tb, const ScanParams& p,
+                                 const TailParams& t) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = dim3(kScanThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[2];
+    cudaLaunchAttribute attr[3];
     int n = 0;
     if (cluster > 1) {
         attr[n].id = cudaLaunchAttributeClusterDimension;
@@ -241,6 +245,11 @@ static cudaError_t launch_kernel(Kern kern, dim3 grid, uint32_t smem, cudaStream
     if (cooperative) {
         attr[n].id = cudaLaunchAttributeCooperative;
         attr[n].val.cooperative = 1;
+        ++n;
+    }
+    if (pdl) {
+        attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n].val.programmaticStreamSerializationAllowed = 1;
         ++n;
     }
     cfg.attrs = attr;
@@ -355,6 +364,8 @@ static int run_step(mpr_context* h, const mpr_retrieve_args& a, float* dump, cud
                           ? 0 : h->first_wait_ns;
     p.dbg = h->dbg_counters ? h->d_dbg : nullptr;
     p.dbg_ts = h->d_dbg ? h->d_dbg + 8 : nullptr;
+    p.dbg_ring = h->d_dbg ? h->d_dbg + kDbgRingOff : nullptr;
+    p.launch_seq = h->launch_seq++;
     p.dump = dump;
     p.err = h->d_err;
 
@@ -396,11 +407,14 @@ static int run_step(mpr_context* h, const mpr_retrieve_args& a, float* dump, cud
 
     const bool prof = h->prof_used >= 0 && 2 * (h->prof_used + 1) <= static_cast<int>(h->prof_events.size());
     if (prof) CUDA_TRY(h, cudaEventRecord(h->prof_events[2 * h->prof_used], st));
-    const bool coop = fused_tail && h->cooperative;
+    // a plain launch with programmatic stream serialization when asked for (MPR_PDL=1): the grid barrier then relies on
+    // the grid being one wave (it is: grid <= SM count, one CTA per SM) instead of the cooperative-launch guarantee
+    const bool pdl = h->pdl && !kDump && !pair;
+    const bool coop = fused_tail && h->cooperative && !pdl;
     cudaError_t le;
     const uint32_t sm = pl.smem_bytes;
 #define MPR_LAUNCH(DUMP, CL, QT, FQ, RL, COOP) \
-    launch_kernel(scan_topk_kernel<DUMP, CL, QT, FQ, RL>, grid, sm, st, CL, COOP, tq, tb, p, t)
+    launch_kernel(scan_topk_kernel<DUMP, CL, QT, FQ, RL>, grid, sm, st, CL, COOP, pdl, tq, tb, p, t)
     if (pl.reg_list && !kDump) {
         if (pair)                     le = MPR_LAUNCH(false, 2, false, false, true, false);
         else if (pl.q_tmem && raw)    le = MPR_LAUNCH(false, 1, true, true, true, coop);
@@ -528,6 +542,7 @@ int mpr_create(int device, mpr_handle_t* out) {
         if (flag("MPR_NO_REGLIST")) h->use_reg_list = 0;
         if (flag("MPR_NO_TAIL_FLOOR")) h->tail_floor = 0;
         if (flag("MPR_NO_QCOOP")) h->q_coop = 0;
+        if (flag("MPR_PDL")) h->pdl = 1;
         const char* tr = getenv("MPR_THR_REPLICAS");
         if (tr) h->thr_rep_log2 = tr[0] == '1' ? 0 : tr[0] == '2' ? 1 : 2;
         const char* fw = getenv("MPR_FIRST_WAIT_NS");
@@ -620,6 +635,17 @@ int mpr_debug_timeline(mpr_handle_t h, uint64_t* out, int n_ctas) {
     if (!h->d_dbg) return MPR_OK;
     DeviceGuard guard(h->device);
     CUDA_TRY(h, cudaMemcpy(out, h->d_dbg + 8, sizeof(uint64_t) * 24 * n_ctas, cudaMemcpyDeviceToHost));
+    return MPR_OK;
+}
+
+int mpr_debug_launch_ring(mpr_handle_t h, uint64_t* out128, unsigned* next_seq) {
+    if (!h || !out128) return fail(h, MPR_EINVAL, "bad argument");
+    memset(out128, 0, sizeof(uint64_t) * 128);
+    if (next_seq) *next_seq = h->launch_seq;
+    if (!h->d_dbg) return MPR_OK;
+    DeviceGuard guard(h->device);
+    CUDA_TRY(h, cudaMemcpy(out128, h->d_dbg + kDbgRingOff, sizeof(uint64_t) * 128, cudaMemcpyDeviceToHost));
+    CUDA_TRY(h, cudaMemset(h->d_dbg + kDbgRingOff, 0, sizeof(uint64_t) * 128));
     return MPR_OK;
 }
 

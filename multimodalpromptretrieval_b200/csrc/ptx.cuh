@@ -129,6 +129,13 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
     return r;
 }
+// Programmatic dependent launch: a kernel launched with programmaticStreamSerialization may start while its
+// predecessor in the stream is still running; griddep_wait() blocks until that predecessor has completed and its
+// memory is visible, griddep_launch_dependents() lets the successor's CTAs be scheduled once every CTA of this grid
+// has issued it (they still need a free SM).
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ void cluster_sync() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }

@@ -100,6 +100,8 @@ struct ScanParams {
     unsigned long long* dbg;  // debug counters (MPR_DEBUG_COUNTERS=1) or nullptr: [0] candidates admitted, [1] warp flushes,
                            // [2] slow-path 8-groups (per warp), [3] list replacements, [4] warp-tiles, [5] threshold refreshes that found a bound
     unsigned long long* dbg_ts;  // debug timeline (MPR_DEBUG_COUNTERS=1|2) or nullptr: [16 * cta + event]
+    unsigned long long* dbg_ring;  // debug: per-launch [first CTA entry (stored as 2^63 - t), last CTA exit] x 64, or nullptr
+    unsigned launch_seq;   // host-side launch counter (selects the ring entry)
     float* dump;           // debug: [b_total][n_local] scores, or nullptr
     int* err;              // device word that receives the code of a starved barrier
 };
@@ -198,6 +200,8 @@ __global__ void __launch_bounds__(kScanThreads, 1)
 scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_bank,
                  const ScanParams p, const TailParams tail) {
     extern __shared__ uint8_t smem_raw[];
+    if (p.dbg_ring && threadIdx.x == 0)
+        atomicMax(p.dbg_ring + 2 * (p.launch_seq & 63u), (1ull << 63) - ptx::globaltimer_ns());
     const uint32_t raw_addr = ptx::smem_u32(smem_raw);
     const uint32_t base = (raw_addr + 1023u) & ~1023u;   // SWIZZLE_128B atoms need 1024-byte alignment
     uint8_t* smem = smem_raw + (base - raw_addr);
@@ -261,6 +265,13 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     __syncthreads();
     if constexpr (kCluster > 1) ptx::cluster_sync();      // peers' barriers exist before anything remote touches them
     ptx::tc_fence_after();
+    // Programmatic dependent launch (no-ops without the launch attribute): everything above touched only this CTA's
+    // shared and tensor memory, so it may overlap the previous kernel of the stream — typically the previous retrieval
+    // step, whose last CTAs are still in their tail when this one's first CTAs get an SM.  From here on global memory
+    // is read (queries, control words the previous step re-zeroed, its result buffers are overwritten): wait for it.
+    // The successor may be scheduled as soon as every CTA of this grid is resident (they all pass this point).
+    ptx::griddep_wait();
+    ptx::griddep_launch_dependents();
     const uint32_t tmem_base = *tmem_slot;
     // debug timeline (MPR_DEBUG_COUNTERS=1): dbg[8 + 16*cta + k] = globaltimer at event k of this CTA
     auto stamp = [&](int k) {
@@ -995,6 +1006,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             if (threadIdx.x == 0) tail_ticket(tail, e, gridDim.x);
         }
     }
+    if (p.dbg_ring && threadIdx.x == 0) atomicMax(p.dbg_ring + 2 * (p.launch_seq & 63u) + 1, ptx::globaltimer_ns());
 }
 
 }  // namespace mpr

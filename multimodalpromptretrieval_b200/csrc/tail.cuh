@@ -181,21 +181,26 @@ __device__ __forceinline__ void store_merged(uint64_t elem, int q, int kk, int l
 // ------------------------------------------------------------------------------------------------ peer-memory exchange
 // Every rank owns one exchange buffer of identical layout, mapped into every peer (symmetric memory), zero-filled once:
 //
-//   byte 0      u32 epoch                 last exchange this rank has fully consumed
-//   byte 4      u32 done                  tail tickets of the launch in flight (stand-alone tail kernel only)
-//   byte 1024   u32 flag[world][cap]      flag[r][q] = newest epoch whose query-q candidates rank r delivered INTO THIS buffer
-//   then        u64 slot[2][world][cap]   candidate lists ([q][kk] inside a slot), double-buffered on epoch parity
+//   byte 0      u32 epoch                  last exchange this rank has fully consumed
+//   byte 4      u32 done                   tail tickets of the launch in flight (stand-alone tail kernel only)
+//   byte 1024   u64 word[2][world][cap][2] candidate lists ([q][kk] keys inside a [rank] block, two words per key),
+//                                          double-buffered on epoch parity
 //
-// Exchange e = epoch + 1.  For query q a warp stores its kk keys into slot[e&1][my_rank] of EVERY rank's buffer,
-// fences (fence.sys) and releases flag[my_rank][q] = e on every rank; then it waits (ld.acquire.sys) until its own
-// buffer shows flag[r][q] >= e for all r and merges slot[e&1][0..world) in rank order (= global row order, so ties still
-// resolve to the lower row).  The last warp of the launch publishes epoch = e.
-// Why two slots are enough: a rank can start exchange e+1 (writing slot[(e+1)&1]) while a slow peer still reads
-// slot[e&1], but it cannot reach e+2 before that peer has delivered its own e+1 flags, which it does only after its
+// Exchange e = epoch + 1.  A key travels as TWO self-validating 8-byte words, {low half | e << 32} and
+// {high half | e << 32}: an aligned 8-byte store is single-copy atomic, so a reader that finds tag e in a word has that
+// word's payload — no fence, no separate flag, no second NVLink round trip (the flag + fence.sys protocol this replaces
+// cost a store round trip, a system fence and a flag round trip per step).  For query q a warp stores its kk keys into
+// word[e&1][my_rank] of EVERY rank's buffer (one 16-byte store per key and peer), then polls word[e&1][0..world) of its
+// OWN buffer until every word carries tag e and merges the world lists (keys are unique — they embed the global row — so
+// the merge is order-independent and ties still resolve to the lower row).  The last warp of the launch publishes
+// epoch = e.  Stale words carry an older tag (or 0) whatever batch shape wrote them.
+// Why two parities are enough: a rank can start exchange e+1 (writing word[(e+1)&1]) while a slow peer still reads
+// word[e&1], but it cannot reach e+2 before that peer has delivered its own e+1 words, which it does only after its
 // merge of e.  The waiting warp only ever waits on OTHER GPUs, never on a kernel that must be co-scheduled on its own.
 // Sharded search is therefore a COLLECTIVE call: every rank must issue the same sequence of searches.
 constexpr int kXchgMaxWorld = 16;
-constexpr int kXchgFlagOff = 1024;
+constexpr int kXchgDataOff = 1024;
+constexpr int kXchgMaxPerLane = kXchgMaxWorld * 32 / 32;      // world * kk <= 512 keys, spread over 32 lanes
 constexpr int kErrXchgTimeout = 201;
 
 struct XchgPeers {
@@ -208,20 +213,15 @@ struct XchgParams {
     XchgPeers peers;               // peers.buf[rank] = this rank's own buffer
 };
 
-__host__ __device__ inline size_t xchg_slot_off(int world, int cap) {
-    return (static_cast<size_t>(kXchgFlagOff) + static_cast<size_t>(world) * cap * sizeof(uint32_t) + 15u) & ~size_t(15);
-}
 __host__ __device__ inline size_t xchg_bytes(int world, int cap) {
-    return xchg_slot_off(world, cap) + 2ull * world * cap * sizeof(uint64_t);
+    return static_cast<size_t>(kXchgDataOff) + 2ull * world * cap * 2ull * sizeof(uint64_t);
 }
 
-__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
+__device__ __forceinline__ void st_relaxed_sys_v2_u64(uint64_t* p, uint64_t a, uint64_t b) {
+    asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
 }
-__device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void ld_relaxed_sys_v2_u64(const uint64_t* p, uint64_t& a, uint64_t& b) {
+    asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
 }
 __device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const uint32_t* p) {
     uint32_t v;
@@ -229,43 +229,78 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const uint32_t* p) {
     return v;
 }
 
+// Top-kk of up to 32 * kN keys held in registers (0 = empty), any order: pivot from the lane maxima, then inserts.
+template <int kN>
+__device__ __forceinline__ uint64_t warp_merge_regs(const uint64_t (&key)[kN], int kk, int lane) {
+    uint64_t lm = key[0];
+#pragma unroll
+    for (int u = 1; u < kN; ++u) lm = key[u] > lm ? key[u] : lm;
+    int rank = 0;
+    for (int o = 1; o < 32; ++o) rank += shfl_u64(lm, (lane + o) & 31) > lm ? 1 : 0;
+    const unsigned who = __ballot_sync(kFullMask, rank == kk - 1 && lm != 0ull);
+    const uint64_t floor = who ? shfl_u64(lm, __ffs(who) - 1) - 1ull : 0ull;
+    uint64_t elem = 0ull, kth = floor;
+#pragma unroll
+    for (int u = 0; u < kN; ++u) {
+        unsigned pending = __ballot_sync(kFullMask, key[u] > kth);
+        while (pending) {
+            const int src = __ffs(pending) - 1;
+            pending &= pending - 1;
+            const uint64_t cand = shfl_u64(key[u], src);
+            if (cand > kth) {    // uniform: the threshold may have moved since the ballot
+                elem = warp_list_insert(elem, cand, lane);
+                const uint64_t last = shfl_u64(elem, kk - 1);
+                kth = last > floor ? last : floor;
+            }
+        }
+    }
+    return elem;
+}
+
 // Exchange of one query's merged local list (`elem`, one element per lane) with all ranks; returns the global list.
 // `e` is the exchange epoch of this launch.  On a timeout *status receives kErrXchgTimeout and the LOCAL list is returned.
 __device__ __forceinline__ uint64_t warp_exchange(const XchgParams& x, uint32_t e, uint64_t elem, int q, int kk, int lane,
                                                   int* status) {
-    const size_t slot_off = xchg_slot_off(x.world, x.cap);
-    const size_t slot = (static_cast<size_t>(e & 1u) * x.world + x.rank) * x.cap + static_cast<size_t>(q) * kk;
+    const uint64_t tag = static_cast<uint64_t>(e) << 32;
+    const size_t parity_off = static_cast<size_t>(e & 1u) * x.world * x.cap * 2;      // in words
     if (lane < kk) {
+        const uint64_t w0 = (elem & 0xFFFFFFFFull) | tag, w1 = (elem >> 32) | tag;
+        const size_t off = parity_off + (static_cast<size_t>(x.rank) * x.cap + static_cast<size_t>(q) * kk + lane) * 2;
         for (int r = 0; r < x.world; ++r)
-            reinterpret_cast<uint64_t*>(x.peers.buf[r] + slot_off)[slot + lane] = elem;
+            st_relaxed_sys_v2_u64(reinterpret_cast<uint64_t*>(x.peers.buf[r] + kXchgDataOff) + off, w0, w1);
     }
-    __threadfence_system();
-    __syncwarp();
-    if (lane < x.world)
-        st_release_sys_u32(reinterpret_cast<uint32_t*>(x.peers.buf[lane] + kXchgFlagOff) +
-                               static_cast<size_t>(x.rank) * x.cap + q, e);
-    unsigned char* mine = x.peers.buf[x.rank];
+    const uint64_t* mine = reinterpret_cast<const uint64_t*>(x.peers.buf[x.rank] + kXchgDataOff) + parity_off;
+    const int total = x.world * kk;
+    uint64_t ent[kXchgMaxPerLane];
+    unsigned need = 0u;
+#pragma unroll
+    for (int j = 0; j < kXchgMaxPerLane; ++j) {
+        ent[j] = 0ull;
+        if (lane + 32 * j < total) need |= 1u << j;
+    }
+    const uint64_t t0 = ptx::globaltimer_ns();
     bool ok = true;
-    if (lane < x.world) {
-        const uint32_t* flag = reinterpret_cast<const uint32_t*>(mine + kXchgFlagOff) + static_cast<size_t>(lane) * x.cap + q;
-        if (static_cast<int32_t>(ld_acquire_sys_u32(flag) - e) < 0) {
-            const uint64_t t0 = ptx::globaltimer_ns();
-            uint32_t polls = 0;
-            while (static_cast<int32_t>(ld_acquire_sys_u32(flag) - e) < 0) {
-                if ((++polls & 0xFFu) == 0 && ptx::globaltimer_ns() - t0 > x.timeout_ns) {
-                    ok = false;
-                    break;
+    for (uint32_t polls = 0;; ++polls) {
+#pragma unroll
+        for (int j = 0; j < kXchgMaxPerLane; ++j) {
+            if (need & (1u << j)) {
+                const int idx = lane + 32 * j, r = idx / kk, i = idx - r * kk;
+                uint64_t a, b;
+                ld_relaxed_sys_v2_u64(mine + (static_cast<size_t>(r) * x.cap + static_cast<size_t>(q) * kk + i) * 2, a, b);
+                if ((a >> 32) == e && (b >> 32) == e) {
+                    ent[j] = (b << 32) | (a & 0xFFFFFFFFull);
+                    need &= ~(1u << j);
                 }
             }
         }
+        if (!__any_sync(kFullMask, need != 0u)) break;
+        if ((polls & 0x3Fu) == 0x3Fu && ptx::globaltimer_ns() - t0 > x.timeout_ns) ok = false;
+        if (!__all_sync(kFullMask, ok)) {
+            if (lane == 0 && status) atomicMax(status, kErrXchgTimeout);
+            return elem;
+        }
     }
-    if (!__all_sync(kFullMask, ok)) {
-        if (lane == 0 && status) atomicMax(status, kErrXchgTimeout);
-        return elem;
-    }
-    const uint64_t* slots = reinterpret_cast<const uint64_t*>(mine + slot_off) +
-                            static_cast<size_t>(e & 1u) * x.world * x.cap + static_cast<size_t>(q) * kk;
-    return warp_merge_lists<true>(slots, x.world, x.cap, 1ll, kk, lane);
+    return warp_merge_regs<kXchgMaxPerLane>(ent, kk, lane);
 }
 
 // ------------------------------------------------------------------------------------------------ vote + prompt ids

@@ -294,6 +294,20 @@ def debug_timeline(n_ctas: int, device: Optional[int] = None):
     return np.where(a > 0, a - t0, -1)
 
 
+def debug_launch_ring(device: Optional[int] = None):
+    """(entry_ns, exit_ns) of the most recent scan launches, oldest first (MPR_DEBUG_COUNTERS=1|2); clears the ring."""
+    h = handle(device)
+    out = (C.c_uint64 * 128)()
+    seq = C.c_uint(0)
+    h.check(h.lib.mpr_debug_launch_ring(h.ptr, out, C.byref(seq)), "mpr_debug_launch_ring")
+    res = []
+    for s_ in range(max(0, seq.value - 64), seq.value):
+        first, last = int(out[2 * (s_ % 64)]), int(out[2 * (s_ % 64) + 1])
+        if first and last:
+            res.append(((1 << 63) - first, last))
+    return res
+
+
 def last_launch_count(device: Optional[int] = None) -> int:
     h = handle(device)
     return int(h.lib.mpr_last_launch_count(h.ptr))

@@ -73,7 +73,8 @@ class CandidateExchange:
 class P2PExchange:
     """Peer-memory candidate exchange: one symmetric-memory buffer per rank, mapped into every peer.  The exchange itself
     runs inside the retrieval kernel's tail (csrc/tail.cuh): a warp stores its query's candidates straight into every
-    peer's buffer over NVLink, raises a per-query flag, waits for the peers' flags and merges — no collective library on
+    peer's buffer over NVLink as epoch-tagged 8-byte words, polls its own buffer for the peers' words and merges — no
+    fence, no flag, no collective library on
     the data path, epoch kept on the device.  This class only owns the buffer and the table of peer pointers the C ABI
     takes (``mpr_retrieve_args.peer_bufs``).  ``cap`` (>= b * kk of any search) is fixed at construction: growing it
     would be an implicit collective (rendezvous + barrier) in the middle of a search.

@@ -463,7 +463,7 @@ def K_handle_ok():
 def test_p2p_exchange_protocol_on_one_gpu(K, world, b):
     """The peer-memory exchange of the retrieval tail (csrc/tail.cuh) with the OTHER ranks' deliveries pre-populated in
     the exchange buffer (nothing here ever waits on a kernel that has not finished): rank r of `world` scans its shard,
-    pushes its lists, finds every peer's flags already raised and merges — the result must equal the unsharded search,
+    pushes its lists, finds every peer's tagged words already in place and merges — the result must equal the unsharded search,
     bit for bit, over several epochs (both slot parities).  (world 2, b 300) is more than one wave of CTAs and takes the
     two-launch path (stand-alone tail kernel)."""
     from multimodalpromptretrieval_b200 import _native
@@ -478,9 +478,8 @@ def test_p2p_exchange_protocol_on_one_gpu(K, world, b):
     me = world // 2
     x = P2PExchange(dev(), cap, world_size=world, rank=me)
     nbytes = K.exchange_bytes(world, cap)
-    flag_off = 1024
-    slot_off = (flag_off + world * cap * 4 + 15) // 16 * 16
-    assert nbytes == slot_off + 2 * world * cap * 8
+    data_off = 1024
+    assert nbytes == data_off + 2 * world * cap * 16          # two tagged 8-byte words per key, two parities
     b0, b1 = shard_bounds(n, me, world)
     shard, sbias = bd[b0:b1].contiguous(), bias[b0:b1].contiguous()
     ws = K.new_workspace(K.search_workspace_bytes(b, b1 - b0, d, kk), dev())
@@ -490,17 +489,18 @@ def test_p2p_exchange_protocol_on_one_gpu(K, world, b):
     for epoch in range(1, 4):
         q = torch.cat([bank[:b // 2].clone(), clip_like(b - b // 2, d, 40 + epoch)]).to(dev())
         full_keys, _, full_idx = K.search_topk(q, bd, bias, kk)
-        # what the peers would have delivered: their shard's lists into slot[epoch & 1][r], flags = epoch
+        # what the peers would have delivered: their shard's lists into word[epoch & 1][r] as {key half | epoch << 32}
         host = x.buf.cpu().numpy().copy()
-        flags = host[flag_off:flag_off + world * cap * 4].view(np.uint32).reshape(world, cap)
-        slots = host[slot_off:].view(np.uint64).reshape(2, world, cap)
+        words = host[data_off:].view(np.uint64).reshape(2, world, cap, 2)
         for r in range(world):
             if r == me:
                 continue
             r0, r1 = shard_bounds(n, r, world)
             k_r, _, _ = K.search_topk(q, bd[r0:r1].contiguous(), bias[r0:r1].contiguous(), kk, idx_base=r0)
-            slots[epoch & 1, r, :b * kk] = k_r.cpu().numpy().view(np.uint64).reshape(-1)
-            flags[r, :b] = epoch
+            keys = k_r.cpu().numpy().view(np.uint64).reshape(-1)
+            tag = np.uint64(epoch) << np.uint64(32)
+            words[epoch & 1, r, :b * kk, 0] = (keys & np.uint64(0xFFFFFFFF)) | tag
+            words[epoch & 1, r, :b * kk, 1] = (keys >> np.uint64(32)) | tag
         x.buf.copy_(torch.from_numpy(host))
         a = _native.RetrieveArgs()
         a.q_bf16, a.b, a.bank, a.bias = q.data_ptr(), b, shard.data_ptr(), sbias.data_ptr()

@@ -23,6 +23,12 @@ torch.cuda.synchronize()
 print(f"b={b} n={n} d={d} kk={kk}: {e0.elapsed_time(e1) / 5 * 1e3:.1f} us/step, counters={K.debug_counters()}")
 if os.environ.get("MPR_DEBUG_COUNTERS"):
     import numpy as np
+    ring = K.debug_launch_ring()
+    if len(ring) >= 3:
+        dur = [(b_ - a_) / 1e3 for a_, b_ in ring]
+        gap = [(ring[i + 1][0] - ring[i][1]) / 1e3 for i in range(len(ring) - 1)]
+        print("  launch durations (first instruction -> last instruction), us:", " ".join(f"{x:.1f}" for x in dur[-6:]))
+        print("  gaps between consecutive launches, us:", " ".join(f"{x:.1f}" for x in gap[-5:]))
     pl = K.search_plan(b, n, d, kk)
     tl = K.debug_timeline(pl["n_ctas"]) / 1e3          # us
     names = ["entry", "q_ready", "producer_done", "g0_loop_end", "g0_written", "g1_loop_end", "g1_written", "cta_done",

@@ -54,9 +54,11 @@ full, _, _ = K.search_topk(q, bank, bias, kk)
 x = P2PExchange(dev, cap, world_size=2, rank=0)
 other, _, _ = K.search_topk(q, bank[n // 2:].contiguous(), bias[n // 2:].contiguous(), kk, idx_base=n // 2)
 host = x.buf.cpu().numpy().copy()
-flag_off, slot_off = 1024, (1024 + 2 * cap * 4 + 15) // 16 * 16
-host[flag_off:flag_off + 2 * cap * 4].view(np.uint32).reshape(2, cap)[1, :b] = 1
-host[slot_off:].view(np.uint64).reshape(2, 2, cap)[1, 1, :b * kk] = other.cpu().numpy().view(np.uint64).reshape(-1)
+words = host[1024:].view(np.uint64).reshape(2, 2, cap, 2)        # [parity][rank][key][half], tagged with the epoch (1)
+okeys = other.cpu().numpy().view(np.uint64).reshape(-1)
+tag = np.uint64(1) << np.uint64(32)
+words[1, 1, :b * kk, 0] = (okeys & np.uint64(0xFFFFFFFF)) | tag
+words[1, 1, :b * kk, 1] = (okeys >> np.uint64(32)) | tag
 x.buf.copy_(torch.from_numpy(host))
 ws = K.new_workspace(K.search_workspace_bytes(b, n // 2, d, kk), dev)
 out = torch.empty((b, kk), dtype=torch.int64, device=dev)
