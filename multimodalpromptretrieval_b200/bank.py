@@ -85,7 +85,9 @@ class _Step:
         # device staging for host-resident query halves, one pair per turn (a queued step reads its own pair)
         self.q0 = [torch.empty((b, d0), dtype=dtype, device=dev) for _ in range(2)]
         self.q1 = [torch.empty((b, d1), dtype=dtype, device=dev) if d1 else None for _ in range(2)]
-        self.q_scratch = torch.empty((b, d), dtype=torch.bfloat16, device=dev) if d > 512 and b > 128 else None
+        # bf16 copy of raw queries for the scan variants that take prepared rows (hybrid q-tile: 512 < D <= 1024 with more
+        # than 16 queries; CTA-pair multicast for wider rows)
+        self.q_scratch = torch.empty((b, d), dtype=torch.bfloat16, device=dev) if d > 512 and b > 16 else None
         n_local = bank.retrieval_embeddings.shape[0]
         need = K.search_workspace_bytes(b, n_local, d, kk, dev.index)
         if need == 0:

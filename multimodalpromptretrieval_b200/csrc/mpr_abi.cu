@@ -4,6 +4,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -45,6 +46,8 @@ struct mpr_context {
     int use_reg_list = 1;                   // k + skip <= 8: lists in registers (MPR_NO_REGLIST=1: shared memory)
     int first_wait_ns = 16000;              // first tile: bounded wait for the shared thresholds (MPR_FIRST_WAIT_NS; -1 = legacy start)
     int thr_rep_log2 = 2;                   // up to 4 replica words per threshold slot (MPR_THR_REPLICAS=1|2|4)
+    int hybrid_min_b = 16;                  // ... for batches beyond this many queries (MPR_HYBRID_MIN_B)
+    int use_hybrid = 1;                     // hybrid TMEM + shared-memory q-tile for 512 < D <= 1024 (MPR_NO_HYBRID=1 disables)
     int pdl = 0;                            // programmatic dependent launch of the scan kernel (MPR_PDL=1)
     int q_coop = 1;                         // warp-cooperative coalesced q-tile fill (MPR_NO_QCOOP=1: a thread per row)
     int tail_floor = 1;                     // pool merge drops keys below the final shared threshold (MPR_NO_TAIL_FLOOR=1)
@@ -103,11 +106,13 @@ struct DeviceGuard {
 struct ScanPlan {
     int n_chunks, q_tile, q_box_rows, n_qtiles, n_splits, n_tiles, n_stages, kk_pad, cand_cap, sub_per_stage, n_epi_groups;
     bool q_tmem;       // q-tile in tensor memory (TMEM A operand) instead of shared memory
+    bool hybrid;       // 512 < D <= 1024: K-chunks 0..7 of the q-tile in tensor memory, the rest in shared memory
+    int n_q_smem;      // K-chunks of the q-tile held in shared memory
     bool reg_list;     // k + skip <= 8: per-query lists in registers (no list / pending memory in shared memory)
     uint32_t smem_bytes;
 };
 
-static int make_plan(mpr_context* h, int b, int64_t n_local, int d, int kk, ScanPlan* pl) {
+static int make_plan(mpr_context* h, int b, int64_t n_local, int d, int kk, ScanPlan* pl, bool allow_hybrid = true) {
     if (b < 1) return fail(h, MPR_EINVAL, "b must be >= 1 (got %d)", b);
     if (n_local < 0 || n_local >= (1ll << 31) - kTileRows)      // 0 = a rank whose shard is empty still takes part in the exchange
         return fail(h, MPR_EINVAL, "n_local out of range (got %lld)", static_cast<long long>(n_local));
@@ -120,6 +125,12 @@ static int make_plan(mpr_context* h, int b, int64_t n_local, int d, int kk, Scan
     pl->n_tiles = static_cast<int>((n_local + kTileRows - 1) / kTileRows);
     // D <= 512: the q-tile (128 x D bf16) fits 256 TMEM columns next to two 128-column accumulators
     pl->q_tmem = h->use_q_tmem && d <= 512;
+    // 512 < D <= 1024 with more than 64 queries: a q-tile in shared memory alone would have to shrink to 64 queries
+    // (M = 64 MMAs at half the tensor rate, the bank read once more per extra q-tile).  The hybrid q-tile keeps 128
+    // queries resident: the first 512 dims in tensor memory, the remaining <= 512 in shared memory (<= 128 KiB).
+    pl->hybrid = allow_hybrid && h->use_hybrid && h->use_q_tmem && h->q_coop && d > 512 && d <= 1024 && b > h->hybrid_min_b;
+    if (pl->hybrid) pl->q_tmem = true;
+    pl->n_q_smem = pl->hybrid ? pl->n_chunks - kQTmemChunks : (pl->q_tmem ? 0 : pl->n_chunks);
     int q_tile_max = 128;
     while (!pl->q_tmem && q_tile_max > 8 && static_cast<long long>(q_tile_max) * d * 2 > 131072) q_tile_max >>= 1;
     // Shared memory is split between the resident q-tile, the per-query lists and the bank ring.  Reading the bank
@@ -136,16 +147,26 @@ static int make_plan(mpr_context* h, int b, int64_t n_local, int d, int kk, Scan
             pl->n_qtiles = (b + q_tile_max - 1) / q_tile_max;
             pl->q_box_rows = q_tile_max;
         }
-        if (pl->q_tmem) pl->q_box_rows = 0;       // nothing of Q in shared memory
+        // D <= 512: nothing of Q in shared memory; hybrid: 64- or 128-row slabs for the dims beyond 512
+        if (pl->q_tmem) {
+            pl->q_box_rows = 0;
+            if (pl->hybrid) {      // slab rows: the batch rounded up to 16, and >= 32 KiB in all (the fill's scratch)
+                int rows = (std::min(b, 128) + 15) / 16 * 16;
+                const int min_rows = ((256 + pl->n_q_smem - 1) / pl->n_q_smem + 15) / 16 * 16;
+                pl->q_box_rows = std::min(128, std::max(rows, min_rows));
+            }
+        }
         // Two epilogue groups (two lists per query) unless the second group's lists would starve the bank ring
         // (SS mode keeps 64-128 KiB of Q in shared memory, and a k+s = 32 list is 392 B per query).  With the shared
         // admission thresholds list maintenance is off the critical path for every k, so k no longer decides this.
         // (deeper pending buffers were measured to HURT: 32 slots -> +25 % at k+s = 16/32, because the admission
         // threshold only moves at a flush and a stale threshold admits many more candidates)
         const int caps1[] = {16, 14, 12, 10, 10}, caps2[] = {16, 14, 12, 10};
-        const int caps0[] = {16};                      // register lists: only the pending buffer lives in shared memory
+        // register lists: only the pending buffer lives in shared memory; beside a hybrid q-tile (128 KiB of shared
+        // memory) the smallest buffer buys a fourth ring stage, which the L2-latency-bound B-operand stream needs more
+        const int caps0[] = {pl->hybrid ? 10 : 16};
         auto units_for = [&](int cap, int groups) {   // 16 KiB ring units left beside the resident q-tile and the lists
-            const ScanSmemLayout fixed = scan_smem_layout(pl->n_chunks, pl->q_box_rows, pl->kk_pad, cap, 0, 1, groups);
+            const ScanSmemLayout fixed = scan_smem_layout(pl->n_q_smem, pl->q_box_rows, pl->kk_pad, cap, 0, 1, groups);
             return (kMaxSmem - 1024 - static_cast<int>(fixed.total)) / kStageBytes;
         };
         pl->n_epi_groups = (!pl->reg_list && units_for(16, 2) < 6) ? 1 : 2;
@@ -171,6 +192,11 @@ static int make_plan(mpr_context* h, int b, int64_t n_local, int d, int kk, Scan
         if (stages >= 3 || q_tile_max <= 32 || pl->q_tmem || pl->q_box_rows < q_tile_max) break;
         q_tile_max >>= 1;
     }
+    if (pl->hybrid) {
+        // the ring needs at least three 16 KiB stages (the q-tile fill's scratch is the shared-memory half of the q-tile
+        // itself: n_q_smem >= 2 slabs of 16 KiB)
+        if (stages < 3 || pl->n_q_smem < 2) return make_plan(h, b, n_local, d, kk, pl, false);
+    }
     if (stages < 2) return fail(h, MPR_EINVAL, "shape does not fit shared memory (d=%d, kk=%d)", d, kk);
     // Group 64-wide K sub-chunks into 32 / 64 KiB ring stages (one barrier round-trip per 8 / 16 MMAs — the MMA warp is
     // otherwise bound by its own barrier + issue overhead) as long as at least three stages remain.
@@ -185,7 +211,7 @@ static int make_plan(mpr_context* h, int b, int64_t n_local, int d, int kk, Scan
     pl->n_splits = h->num_sms / g;
     if (pl->n_splits > pl->n_tiles) pl->n_splits = pl->n_tiles;
     if (pl->n_splits < 1) pl->n_splits = 1;
-    pl->smem_bytes = scan_smem_layout(pl->n_chunks, pl->q_box_rows, pl->kk_pad, pl->cand_cap, stages, pl->sub_per_stage, pl->n_epi_groups).total + 1024u;
+    pl->smem_bytes = scan_smem_layout(pl->n_q_smem, pl->q_box_rows, pl->kk_pad, pl->cand_cap, stages, pl->sub_per_stage, pl->n_epi_groups).total + 1024u;
     return MPR_OK;
 }
 
@@ -264,7 +290,9 @@ static int run_step(mpr_context* h, const mpr_retrieve_args& a, float* dump, cud
     ScanPlan pl;
     const int saved_reg = h->use_reg_list;
     if (kDump) h->use_reg_list = 0;            // the dump epilogue exists for the shared-memory-list variant only
-    int rc = make_plan(h, b, a.n_local, d, kk, &pl);
+    // the hybrid q-tile takes prepared bf16 queries: raw ones go through kernel 1 into the caller's scratch first
+    const bool can_prepare = a.q0 == nullptr || a.q_scratch != nullptr;
+    int rc = make_plan(h, b, a.n_local, d, kk, &pl, !kDump && can_prepare);
     h->use_reg_list = saved_reg;
     if (rc) return rc;
     const WsLayout wl = ws_layout(h, pl, b, kk);
@@ -277,8 +305,8 @@ static int run_step(mpr_context* h, const mpr_retrieve_args& a, float* dump, cud
     const uint16_t* q_bf16 = a.q_bf16;
     // tensor-bound regime with an even number of q-tiles: CTA pairs share each bank chunk by TMA multicast
     bool pair = !kDump && !pl.q_tmem && h->use_cluster && pl.n_qtiles >= 2 && pl.n_qtiles % 2 == 0;
-    if (raw && pair) {
-        if (a.q_scratch) {     // the pair variant takes prepared queries: one kernel-1 launch into the caller's scratch
+    if (raw && (pair || pl.hybrid)) {
+        if (a.q_scratch) {     // these variants take prepared queries: one kernel-1 launch into the caller's scratch
             const int threads = 256, rows_per_block = threads / 32;
             bank_build_kernel<<<(b + rows_per_block - 1) / rows_per_block, threads, 0, st>>>(
                 a.q0, a.d0, a.q1, a.q1 ? a.d1 : 0, a.q_dtype, b, a.normalise, a.q_scratch, a.out_q_bias);
@@ -295,7 +323,7 @@ static int run_step(mpr_context* h, const mpr_retrieve_args& a, float* dump, cud
     if (!raw && !q_bf16) return fail(h, MPR_EINVAL, "no queries: q0 and q_bf16 are both null");
 
     CUtensorMap tq, tb;
-    if (pl.q_tmem || raw) memset(&tq, 0, sizeof(tq));       // the warps bring the q-tile in; no Q tensor map
+    if ((pl.q_tmem && !pl.hybrid) || raw) memset(&tq, 0, sizeof(tq));       // the warps bring the q-tile in; no Q tensor map
     else rc = encode_2d(h, &tq, q_bf16, static_cast<uint64_t>(b), static_cast<uint64_t>(d), pl.q_box_rows);
     if (rc) return rc;
     if (a.n_local > 0) rc = encode_2d(h, &tb, a.bank, static_cast<uint64_t>(a.n_local), static_cast<uint64_t>(d), pair ? kTileRows / 2 : kTileRows);
@@ -325,6 +353,7 @@ static int run_step(mpr_context* h, const mpr_retrieve_args& a, float* dump, cud
     p.b_total = b;
     p.n_local = static_cast<int>(a.n_local);
     p.n_chunks = pl.n_chunks;
+    p.n_q_smem = pl.n_q_smem;
     p.kk = kk;
     p.kk_pad = pl.kk_pad;
     p.cand_cap = pl.cand_cap;
@@ -355,9 +384,10 @@ static int run_step(mpr_context* h, const mpr_retrieve_args& a, float* dump, cud
     p.thr_rep_log2 = wl.rep_log2;
     p.fused_tail = fused_tail ? 1 : 0;
     {
-        const ScanSmemLayout lay = scan_smem_layout(pl.n_chunks, pl.q_box_rows, pl.kk_pad, pl.cand_cap, pl.n_stages,
+        const ScanSmemLayout lay = scan_smem_layout(pl.n_q_smem, pl.q_box_rows, pl.kk_pad, pl.cand_cap, pl.n_stages,
                                                     pl.sub_per_stage, pl.n_epi_groups);
-        p.q_coop = (h->q_coop && pl.q_tmem && !(raw && a.normalise) && lay.bias_off - lay.list_off >= 8u * 4096u) ? 1 : 0;
+        p.q_coop = (h->q_coop && pl.q_tmem && !(raw && a.normalise) &&
+                    (pl.hybrid || lay.bias_off - lay.list_off >= 8u * 4096u)) ? 1 : 0;
     }
     // waiting for the slots only pays when every slot is fed by some list that gets a tile right away
     p.first_wait_ns = (h->first_wait_ns > 0 && (pl.n_splits < wl.ns || pl.n_tiles < 2 * pl.n_splits * pl.n_epi_groups))
@@ -543,6 +573,9 @@ int mpr_create(int device, mpr_handle_t* out) {
         if (flag("MPR_NO_TAIL_FLOOR")) h->tail_floor = 0;
         if (flag("MPR_NO_QCOOP")) h->q_coop = 0;
         if (flag("MPR_PDL")) h->pdl = 1;
+        if (flag("MPR_NO_HYBRID")) h->use_hybrid = 0;
+        const char* hb = getenv("MPR_HYBRID_MIN_B");
+        if (hb && atoi(hb) >= 0) h->hybrid_min_b = atoi(hb);
         const char* tr = getenv("MPR_THR_REPLICAS");
         if (tr) h->thr_rep_log2 = tr[0] == '1' ? 0 : tr[0] == '2' ? 1 : 2;
         const char* fw = getenv("MPR_FIRST_WAIT_NS");
@@ -685,9 +718,15 @@ int mpr_bank_build(mpr_handle_t h, const void* src0, int d0, const void* src1, i
 
 size_t mpr_search_workspace_bytes(mpr_handle_t h, int b, int64_t n_local, int d, int kk) {
     if (!h) return 0;
-    ScanPlan pl;
+    ScanPlan pl, pl2;
     if (make_plan(h, b, n_local, d, kk, &pl)) return 0;
-    return ws_layout(h, pl, b, kk).total;
+    size_t need = ws_layout(h, pl, b, kk).total;
+    // raw queries without a scratch buffer take the non-hybrid plan: size for whichever a later call may choose
+    if (pl.hybrid && make_plan(h, b, n_local, d, kk, &pl2, false) == MPR_OK) {
+        const size_t need2 = ws_layout(h, pl2, b, kk).total;
+        if (need2 > need) need = need2;
+    }
+    return need;
 }
 
 int mpr_search_plan(mpr_handle_t h, int b, int64_t n_local, int d, int kk, int* n_ctas, int* n_splits, int* n_qtiles,

@@ -56,12 +56,16 @@ constexpr int kEpiGroups = 2;                 // epilogue groups; group g owns t
 constexpr int kCandCapMax = 16;               // per-query pending-candidate slots (a flush leaves >= 8 free)
 constexpr int kTileRing = 64;                 // scheduler -> consumers tile-id ring (entries); >= the producer's lead
 constexpr uint32_t kTileEnd = 0xFFFFFFFFu;
+constexpr int kQTmemChunks = 8;               // K-chunks of a q-tile that fit tensor memory (256 columns)
 constexpr int kMaxQChunkBars = 8;             // per-K-chunk "q-tile chunk is in tensor memory" barriers (D <= 512)
 
 struct ScanParams {
     int b_total;       // queries in the batch
     int n_local;       // bank rows in this shard
     int n_chunks;      // D / 64
+    int n_q_smem;      // K-chunks of the q-tile that live in shared memory: all of them without the TMEM q-tile, none
+                       // with it for D <= 512, and chunks 8.. of a HYBRID q-tile (512 < D <= 1024: the first 512 dims in
+                       // tensor memory, the rest in shared memory, so that 128 queries x 1024 dims stay resident at once)
     int kk;            // list length (k + skip), 1..32
     int kk_pad;        // next power of two >= kk
     int cand_cap;      // pending-candidate slots per query (10..16)
@@ -116,7 +120,7 @@ __host__ __device__ inline uint32_t scan_row_stride(int kk_pad, int cand_cap) {
     return (static_cast<uint32_t>(kk_pad) + cand_cap) | 1u;
 }
 
-__host__ __device__ inline ScanSmemLayout scan_smem_layout(int n_chunks, int q_box_rows, int kk_pad, int cand_cap,
+__host__ __device__ inline ScanSmemLayout scan_smem_layout(int n_chunks /* of the q-tile in shared memory */, int q_box_rows, int kk_pad, int cand_cap,
                                                            int n_stages, int sub_per_stage, int n_groups) {
     ScanSmemLayout l;
     l.q_off = 0;
@@ -126,7 +130,7 @@ __host__ __device__ inline ScanSmemLayout scan_smem_layout(int n_chunks, int q_b
     l.ring_off = l.bias_off + kAccBufs * kTileRows * 4u;
     l.scr_off = l.ring_off + kTileRing * 8u;
     l.bar_off = l.scr_off + 2 * kUmmaM * 4u;
-    l.total = l.bar_off + (1 + 2 * kMaxStages + 2 * kAccBufs + kMaxQChunkBars) * 8u + 16u;
+    l.total = l.bar_off + (1 + 2 * kMaxStages + 2 * kAccBufs + kMaxQChunkBars + 1) * 8u + 16u;
     return l;
 }
 
@@ -206,7 +210,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const uint32_t base = (raw_addr + 1023u) & ~1023u;   // SWIZZLE_128B atoms need 1024-byte alignment
     uint8_t* smem = smem_raw + (base - raw_addr);
 
-    const ScanSmemLayout lay = scan_smem_layout(p.n_chunks, p.q_box_rows, p.kk_pad, p.cand_cap, p.n_stages, p.sub_per_stage, p.n_epi_groups);
+    const ScanSmemLayout lay = scan_smem_layout(p.n_q_smem, p.q_box_rows, p.kk_pad, p.cand_cap, p.n_stages, p.sub_per_stage, p.n_epi_groups);
     const uint32_t q_smem = base + lay.q_off;
     const uint32_t stage_smem = base + lay.stage_off;
     uint64_t* lists = reinterpret_cast<uint64_t*>(smem + lay.list_off);
@@ -220,8 +224,9 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     auto bar_tfull = [&](int b) { return bar_base + 8u + 8u * (2 * kMaxStages + b); };
     auto bar_tempty = [&](int b) { return bar_base + 8u + 8u * (2 * kMaxStages + kAccBufs + b); };
     auto bar_qc = [&](int c) { return bar_base + 8u + 8u * (2 * kMaxStages + 2 * kAccBufs + c); };
+    const uint32_t bar_qs = bar_qc(kMaxQChunkBars);       // hybrid q-tile: the shared-memory half has landed (TMA)
     volatile uint32_t* tmem_slot =
-        reinterpret_cast<volatile uint32_t*>(smem + lay.bar_off + (1 + 2 * kMaxStages + 2 * kAccBufs + kMaxQChunkBars) * 8u);
+        reinterpret_cast<volatile uint32_t*>(smem + lay.bar_off + (1 + 2 * kMaxStages + 2 * kAccBufs + kMaxQChunkBars + 1) * 8u);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -242,6 +247,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     // ---- one-time setup
     if (threadIdx.x == 0) {
         ptx::mbar_init(bar_q, kWarpsFillQ ? 8 : 1);      // one arrive per epilogue warp, or the TMA producer's
+        if constexpr (kQTmem) ptx::mbar_init(bar_qs, 1);
         for (int s = 0; s < p.n_stages; ++s) {
             ptx::mbar_init(bar_full(s), 1);
             ptx::mbar_init(bar_empty(s), kCluster);      // one release per consumer CTA of the cluster
@@ -253,7 +259,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         if constexpr (kQTmem)
             for (int c = 0; c < kMaxQChunkBars; ++c) ptx::mbar_init(bar_qc(c), 4);   // the four warps of the chunk's group
         ptx::fence_mbar_init();
-        if constexpr (!kWarpsFillQ) ptx::prefetch_tensormap(&tmap_q);
+        if (!kWarpsFillQ || (kQTmem && p.n_q_smem > 0)) ptx::prefetch_tensormap(&tmap_q);
         if (p.n_tiles > 0) ptx::prefetch_tensormap(&tmap_bank);
     }
     if (threadIdx.x < kTileRing) tile_ring[threadIdx.x] = 0ull;
@@ -318,6 +324,10 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             }
             __syncwarp();
         }
+        // hybrid q-tile: K-chunks 8.. come in by TMA into shared memory whose first 32 KiB serve as the scratch of the
+        // warps' tensor-memory fill — they are fetched once that fill is through (bar_q), right before the first bank
+        // chunk that needs them is requested
+        bool q_smem_pending = kQTmem && !kFuseQ && p.n_q_smem > 0;
         // streamed bank: a ring stage holds up to sub_per_stage 64-wide K sub-chunks and costs ONE barrier round-trip
         const int spp = p.sub_per_stage;
         const uint32_t t_limit = dynamic ? static_cast<uint32_t>(p.n_tiles) : static_cast<uint32_t>(tile_end);
@@ -355,6 +365,19 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             const int t = static_cast<int>(t_cur);
             for (int j0 = 0; j0 < p.n_chunks; j0 += spp) {
                 const int ns = min(spp, p.n_chunks - j0);
+                if constexpr (kQTmem && !kFuseQ) {
+                    if (q_smem_pending && j0 + ns > kQTmemChunks) {
+                        ptx::mbar_wait(bar_q, 0, p.err, kErrQFull);          // every warp is through with the scratch
+                        if (ptx::elect_one()) {
+                            const uint32_t slab_bytes = static_cast<uint32_t>(p.q_box_rows) * 128u;
+                            ptx::mbar_arrive_expect_tx(bar_qs, slab_bytes * p.n_q_smem);
+                            for (int j = 0; j < p.n_q_smem; ++j)
+                                ptx::tma_load_2d(q_smem + j * slab_bytes, &tmap_q, bar_qs, (kQTmemChunks + j) * kChunkK, q0, ptx::kEvictLast);
+                        }
+                        __syncwarp();
+                        q_smem_pending = false;
+                    }
+                }
                 ptx::mbar_wait(bar_empty(s), ph ^ 1u, p.err, kErrEmpty);
                 if (ptx::elect_one()) {
                     ptx::mbar_arrive_expect_tx(bar_full(s), ns * kStageBytes);
@@ -409,7 +432,10 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 if (j0 > 0) ptx::mbar_wait(bar_full(s), ph, p.err, kErrFull);
                 if constexpr (kQTmem) {
                     if (q_by_chunk && lt == 0) {
-                        for (int u = 0; u < ns; ++u) ptx::mbar_wait(bar_qc(j0 + u), 0, p.err, kErrQFull);
+                        for (int u = 0; u < ns; ++u) {
+                            if (j0 + u < kQTmemChunks) ptx::mbar_wait(bar_qc(j0 + u), 0, p.err, kErrQFull);
+                            else if (j0 + u == kQTmemChunks) ptx::mbar_wait(bar_qs, 0, p.err, kErrQFull);   // the shared-memory half
+                        }
                         if (j0 + ns == p.n_chunks && lane == 0) stamp(1);
                     }
                 }
@@ -424,9 +450,14 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                             for (int k = 0; k < kChunkK / 16; ++k) {
                                 const uint64_t db = desc_hi | static_cast<uint64_t>(b_lo + 2u * k);   // +32 B per K-step
                                 if constexpr (kQTmem) {
-                                    // 16 bf16 of K = 8 TMEM columns; sub-chunk j starts at column j*32
-                                    ptx::umma_bf16_ts(d_tmem, tmem_base + j * (kChunkK / 2) + k * 8, db, idesc,
-                                                      (j | k) != 0 ? 1u : 0u);
+                                    if (j < kQTmemChunks) {
+                                        // 16 bf16 of K = 8 TMEM columns; sub-chunk j starts at column j*32
+                                        ptx::umma_bf16_ts(d_tmem, tmem_base + j * (kChunkK / 2) + k * 8, db, idesc,
+                                                          (j | k) != 0 ? 1u : 0u);
+                                    } else {       // hybrid q-tile: this K-chunk's A operand is in shared memory
+                                        const uint64_t da = desc_hi | static_cast<uint64_t>(a_lo0 + (j - kQTmemChunks) * slab_lo + 2u * k);
+                                        ptx::umma_bf16_ss(d_tmem, da, db, idesc, 1u);
+                                    }
                                 } else {
                                     const uint64_t da = desc_hi | static_cast<uint64_t>(a_lo0 + j * slab_lo + 2u * k);
                                     ptx::umma_bf16_ss(d_tmem, da, db, idesc, (j | k) != 0 ? 1u : 0u);
@@ -555,7 +586,9 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 // transposed through 4 KiB of swizzled scratch so that each thread ends up with its own row's 128 bytes.
                 // The sum of squares is taken by the owning thread over the rounded values in the same order as the
                 // per-thread path, so q_bias_out is bit-identical.
-                uint8_t* scr = smem + lay.list_off + (warp - 2) * 4096;
+                // scratch: the list memory, which is not in use yet — or, beside a hybrid q-tile, the head of the q-tile's
+                // shared-memory half, which the producer fills only after this fill (bar_q)
+                uint8_t* scr = smem + (p.n_q_smem > 0 ? lay.q_off : lay.list_off) + (warp - 2) * 4096;
                 const void* s0 = kFuseQ ? p.qsrc0 : static_cast<const void*>(p.q);
                 const void* s1 = kFuseQ ? p.qsrc1 : nullptr;
                 const int sd0 = kFuseQ ? p.qd0 : p.d, sd1 = kFuseQ ? p.qd1 : 0;
@@ -613,7 +646,8 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                         *reinterpret_cast<uint4*>(scr + rl * 128 + ((u ^ (rl & 7)) << 4)) = out;
                     }
                 };
-                for (int c = grp; c < p.n_chunks; c += kEpiGroups) {
+                const int n_tmem_chunks = min(p.n_chunks, kQTmemChunks);
+                for (int c = grp; c < n_tmem_chunks; c += kEpiGroups) {
                     if (sdt == kSrcF32) fill_chunk(std::true_type{}, c);
                     else                fill_chunk(std::false_type{}, c);
                     __syncwarp();
@@ -648,6 +682,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                     ptx::named_bar_sync(4, 256);       // every warp is through with its scratch: the memory becomes lists
                     if (active_group) for (int i = 0; i < kk; ++i) my_list[i] = 0ull;
                 }
+                if (p.n_q_smem > 0) ptx::fence_proxy_async_smem();   // scratch accesses before the TMA that overwrites it
             } else if constexpr (kFuseQ) {
                 auto load_q8 = [&](int col, float (&x)[8]) {      // 8 consecutive elements of [src0 | src1]
                     if (col < p.qd0) load8(p.qsrc0, p.q_dtype, qrow_idx * p.qd0 + col, x);

@@ -101,6 +101,9 @@ TOPK_CASES = [
     (7, 127, 64, 3), (7, 128, 64, 3), (7, 129, 64, 3), (3, 1, 64, 1), (40, 50000, 256, 31),
     (512, 60000, 512, 5), (256, 4000, 1024, 3), (1000, 9000, 512, 2),     # even q-tile counts: CTA-pair multicast path
     (4, 3, 64, 5), (9, 20, 1024, 32),                                     # k > N: fewer rows than list slots
+    # hybrid q-tile (512 < D <= 1024, more than 16 queries): first 512 dims in tensor memory, the rest in shared memory
+    (128, 9000, 1024, 5), (100, 6000, 1024, 32), (200, 5000, 768, 16), (300, 20000, 1024, 5), (66, 400, 576, 8),
+    (17, 3000, 1024, 5), (40, 3000, 640, 2), (50, 70000, 896, 7),
 ]
 
 
@@ -616,6 +619,31 @@ def test_fused_query_cast_with_normalise(K):
     assert (score - score_ref).abs().max().item() < 2e-3                # norm summation order: <= 1 bf16 ulp on few elements
     assert (idx == idx_ref).float().mean().item() > 0.98
     assert (qb + 0.5).abs().max().item() < 5e-3
+
+
+def test_bank_step_with_raw_queries_on_the_hybrid_qtile(tokenizer):
+    """The reference's own row width (512 + 512) with a batch beyond 64 queries: the step prepares the raw halves with
+    kernel 1 into its scratch and scans with the hybrid q-tile; keys equal the two-step search on prepared queries, from
+    device-resident and from host-resident halves alike."""
+    from multimodalpromptretrieval_b200 import kernels as KK
+    from multimodalpromptretrieval_b200.bank import RetrievalBank
+    n, b, k = 7000, 100, 5
+    g = torch.Generator().manual_seed(77)
+    img, txt = torch.randn(n, 512, generator=g) * 0.3, torch.randn(n, 512, generator=g) * 0.3
+    bank = RetrievalBank(tokenizer=tokenizer, shard=False, memoise=False, precomputed_features=True)
+    bank.install_bank([(img.to(dev()), txt.to(dev()))], [str(i % 7) for i in range(n)], None, is_training_phase=False,
+                      retrieval_k=k)
+    qi = (img[:b] + 0.02 * torch.randn(b, 512, generator=g)).contiguous()
+    qt = (txt[:b] + 0.02 * torch.randn(b, 512, generator=g)).contiguous()
+    assert KK.search_plan(b, n, 1024, k)["n_qtiles"] == 1                   # 100 queries x 1024 dims in ONE q-tile
+    q_prepared, _ = KK.bank_build(qi.to(dev()), qt.to(dev()))
+    want, _, _ = KK.search_topk(q_prepared, bank.retrieval_embeddings, bank.bias, k)
+    got_dev = bank.run_step(qi.to(dev()), qt.to(dev()), None, True, False)["device"]["keys"].clone()
+    got_host = bank.run_step(qi.pin_memory(), qt.pin_memory(), None, True, True)["host"]["keys"].clone()
+    assert torch.equal(got_dev, want) and torch.equal(got_host.to(dev()), want)
+    assert (want.cpu().numpy().view(np.uint64) != 0).all()
+    idx = bank.run_step(qi.to(dev()), qt.to(dev()), None, True, False)["device"]["idx"]
+    assert (idx[:, 0].cpu() == torch.arange(b, dtype=torch.int32)).all()    # every query's own row is its nearest
 
 
 def test_recycled_workspace_memory_is_rezeroed(K):

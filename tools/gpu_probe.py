@@ -106,6 +106,9 @@ if os.environ.get("PROBE_AB"):
              (128, 10000000, 512, 5), (16, 1000000, 1024, 16)]
 if os.environ.get("PROBE_LARGE_K"):
     CASES = [(128, 1250000, 512, 16), (128, 1250000, 512, 32), (16, 1250000, 512, 16), (16, 1000000, 1024, 16)]
+if os.environ.get("PROBE_D1024"):
+    CASES = [(64, 1000000, 1024, 5), (128, 1000000, 1024, 5), (128, 1000000, 1024, 16), (256, 1000000, 1024, 5),
+             (1024, 1000000, 1024, 5), (256, 1000000, 768, 5)]
 if os.environ.get("PROBE_FULL"):
     CASES += [(128, 1250000, 512, 1), (128, 1250000, 512, 16), (128, 1250000, 512, 32), (16, 1250000, 512, 32),
               (16, 1000000, 1024, 5), (64, 1000000, 1024, 5), (256, 1000000, 1024, 5), (1, 1250000, 512, 5)]
