@@ -445,7 +445,10 @@ static int run_step(mpr_context* h, const mpr_retrieve_args& a, float* dump, cud
     const uint32_t sm = pl.smem_bytes;
 #define MPR_LAUNCH(DUMP, CL, QT, FQ, RL, COOP) \
     launch_kernel(scan_topk_kernel<DUMP, CL, QT, FQ, RL>, grid, sm, st, CL, COOP, pdl, tq, tb, p, t)
-    if (pl.reg_list && !kDump) {
+    if (pl.hybrid) {
+        if (pl.reg_list) le = launch_kernel(scan_topk_kernel<false, 1, true, false, true, true>, grid, sm, st, 1, coop, pdl, tq, tb, p, t);
+        else             le = launch_kernel(scan_topk_kernel<false, 1, true, false, false, true>, grid, sm, st, 1, coop, pdl, tq, tb, p, t);
+    } else if (pl.reg_list && !kDump) {
         if (pair)                     le = MPR_LAUNCH(false, 2, false, false, true, false);
         else if (pl.q_tmem && raw)    le = MPR_LAUNCH(false, 1, true, true, true, coop);
         else if (pl.q_tmem)           le = MPR_LAUNCH(false, 1, true, false, true, coop);
@@ -555,6 +558,8 @@ int mpr_create(int device, mpr_handle_t* out) {
     opt_in(scan_topk_kernel<false, 1, true, false, true>);
     opt_in(scan_topk_kernel<false, 1, true, true, true>);
     opt_in(scan_topk_kernel<false, 1, false, true, true>);
+    opt_in(scan_topk_kernel<false, 1, true, false, true, true>);
+    opt_in(scan_topk_kernel<false, 1, true, false, false, true>);
     {
         auto flag = [](const char* name) { const char* v = getenv(name); return v && v[0] == '1'; };
         if (flag("MPR_NO_CLUSTER")) h->use_cluster = 0;

@@ -57,7 +57,7 @@ constexpr int kCandCapMax = 16;               // per-query pending-candidate slo
 constexpr int kTileRing = 64;                 // scheduler -> consumers tile-id ring (entries); >= the producer's lead
 constexpr uint32_t kTileEnd = 0xFFFFFFFFu;
 constexpr int kQTmemChunks = 8;               // K-chunks of a q-tile that fit tensor memory (256 columns)
-constexpr int kMaxQChunkBars = 8;             // per-K-chunk "q-tile chunk is in tensor memory" barriers (D <= 512)
+constexpr int kMaxQChunkBars = 8;             // spare barrier slots
 
 struct ScanParams {
     int b_total;       // queries in the batch
@@ -199,7 +199,10 @@ __device__ __forceinline__ float prep_query_row_to_smem(const ScanParams& p, lon
 // only the pending buffer stays in shared memory.  Larger k keeps the list in shared memory as well.
 // kFuseQ: see ScanParams::qsrc0 — replaces /root/reference/dataset/VQAFeatureDataset.py:189-191 in-kernel, for the
 // tensor-memory q-tile (each epilogue thread converts its own row) and the shared-memory one (a warp per row, D <= 2048).
-template <bool kDump, int kCluster, bool kQTmem, bool kFuseQ = false, bool kRegList = false>
+// kHybrid (with kQTmem, prepared queries): K-chunks 8.. of the q-tile are an SS-mode A operand in shared memory.  A
+// compile-time switch because the MMA issue loop is issue-bound in the tensor-bound regime: a run-time branch per MMA
+// group cost cfg4 (4096 x 1 M x 512) 15 %.
+template <bool kDump, int kCluster, bool kQTmem, bool kFuseQ = false, bool kRegList = false, bool kHybrid = false>
 __global__ void __launch_bounds__(kScanThreads, 1)
 scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_bank,
                  const ScanParams p, const TailParams tail) {
@@ -223,8 +226,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     auto bar_empty = [&](int s) { return bar_base + 8u + 8u * (kMaxStages + s); };
     auto bar_tfull = [&](int b) { return bar_base + 8u + 8u * (2 * kMaxStages + b); };
     auto bar_tempty = [&](int b) { return bar_base + 8u + 8u * (2 * kMaxStages + kAccBufs + b); };
-    auto bar_qc = [&](int c) { return bar_base + 8u + 8u * (2 * kMaxStages + 2 * kAccBufs + c); };
-    const uint32_t bar_qs = bar_qc(kMaxQChunkBars);       // hybrid q-tile: the shared-memory half has landed (TMA)
+    const uint32_t bar_qs = bar_base + 8u + 8u * (2 * kMaxStages + 2 * kAccBufs + kMaxQChunkBars);   // hybrid q-tile: the shared-memory half has landed (TMA)
     volatile uint32_t* tmem_slot =
         reinterpret_cast<volatile uint32_t*>(smem + lay.bar_off + (1 + 2 * kMaxStages + 2 * kAccBufs + kMaxQChunkBars + 1) * 8u);
 
@@ -247,7 +249,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     // ---- one-time setup
     if (threadIdx.x == 0) {
         ptx::mbar_init(bar_q, kWarpsFillQ ? 8 : 1);      // one arrive per epilogue warp, or the TMA producer's
-        if constexpr (kQTmem) ptx::mbar_init(bar_qs, 1);
+        if constexpr (kHybrid) ptx::mbar_init(bar_qs, 1);
         for (int s = 0; s < p.n_stages; ++s) {
             ptx::mbar_init(bar_full(s), 1);
             ptx::mbar_init(bar_empty(s), kCluster);      // one release per consumer CTA of the cluster
@@ -256,10 +258,9 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             ptx::mbar_init(bar_tfull(b), 1);
             ptx::mbar_init(bar_tempty(b), 4);   // one arrive per epilogue warp
         }
-        if constexpr (kQTmem)
-            for (int c = 0; c < kMaxQChunkBars; ++c) ptx::mbar_init(bar_qc(c), 4);   // the four warps of the chunk's group
+
         ptx::fence_mbar_init();
-        if (!kWarpsFillQ || (kQTmem && p.n_q_smem > 0)) ptx::prefetch_tensormap(&tmap_q);
+        if constexpr (!kWarpsFillQ || kHybrid) ptx::prefetch_tensormap(&tmap_q);
         if (p.n_tiles > 0) ptx::prefetch_tensormap(&tmap_bank);
     }
     if (threadIdx.x < kTileRing) tile_ring[threadIdx.x] = 0ull;
@@ -327,7 +328,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         // hybrid q-tile: K-chunks 8.. come in by TMA into shared memory whose first 32 KiB serve as the scratch of the
         // warps' tensor-memory fill — they are fetched once that fill is through (bar_q), right before the first bank
         // chunk that needs them is requested
-        bool q_smem_pending = kQTmem && !kFuseQ && p.n_q_smem > 0;
+        bool q_smem_pending = kHybrid;
         // streamed bank: a ring stage holds up to sub_per_stage 64-wide K sub-chunks and costs ONE barrier round-trip
         const int spp = p.sub_per_stage;
         const uint32_t t_limit = dynamic ? static_cast<uint32_t>(p.n_tiles) : static_cast<uint32_t>(tile_end);
@@ -365,7 +366,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             const int t = static_cast<int>(t_cur);
             for (int j0 = 0; j0 < p.n_chunks; j0 += spp) {
                 const int ns = min(spp, p.n_chunks - j0);
-                if constexpr (kQTmem && !kFuseQ) {
+                if constexpr (kHybrid) {
                     if (q_smem_pending && j0 + ns > kQTmemChunks) {
                         ptx::mbar_wait(bar_q, 0, p.err, kErrQFull);          // every warp is through with the scratch
                         if (ptx::elect_one()) {
@@ -408,13 +409,9 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         const uint32_t b_lo0 = (stage_smem >> 4) & 0x3FFFu;
         const uint32_t a_lo0 = (q_smem >> 4) & 0x3FFFu;
         const uint32_t slab_lo = static_cast<uint32_t>(p.q_box_rows) * 8u;      // slab bytes >> 4
-        // with the cooperative fill the q-tile arrives chunk by chunk and the first tile's MMAs follow it chunk by chunk
-        const bool q_by_chunk = kQTmem && p.q_coop;
-        if (!q_by_chunk) {
-            ptx::mbar_wait(bar_q, 0, p.err, kErrQFull);
-            ptx::tc_fence_after();
-            if (lane == 0) stamp(1);
-        }
+        ptx::mbar_wait(bar_q, 0, p.err, kErrQFull);
+        ptx::tc_fence_after();
+        if (lane == 0) stamp(1);
         const int spp = p.sub_per_stage;
         int s = 0;
         uint32_t ph = 0;
@@ -430,14 +427,10 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             for (int j0 = 0; j0 < p.n_chunks; j0 += spp) {
                 const int ns = min(spp, p.n_chunks - j0);
                 if (j0 > 0) ptx::mbar_wait(bar_full(s), ph, p.err, kErrFull);
-                if constexpr (kQTmem) {
-                    if (q_by_chunk && lt == 0) {
-                        for (int u = 0; u < ns; ++u) {
-                            if (j0 + u < kQTmemChunks) ptx::mbar_wait(bar_qc(j0 + u), 0, p.err, kErrQFull);
-                            else if (j0 + u == kQTmemChunks) ptx::mbar_wait(bar_qs, 0, p.err, kErrQFull);   // the shared-memory half
-                        }
-                        if (j0 + ns == p.n_chunks && lane == 0) stamp(1);
-                    }
+                if constexpr (kHybrid) {
+                    // a stage never straddles chunk 8 (sub_per_stage divides 8): the first stage beyond it needs the
+                    // shared-memory half of the q-tile
+                    if (lt == 0 && j0 == kQTmemChunks) ptx::mbar_wait(bar_qs, 0, p.err, kErrQFull);
                 }
                 ptx::tc_fence_after();
                 if (ptx::elect_one()) {
@@ -450,11 +443,11 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                             for (int k = 0; k < kChunkK / 16; ++k) {
                                 const uint64_t db = desc_hi | static_cast<uint64_t>(b_lo + 2u * k);   // +32 B per K-step
                                 if constexpr (kQTmem) {
-                                    if (j < kQTmemChunks) {
+                                    if (!kHybrid || j0 < kQTmemChunks) {
                                         // 16 bf16 of K = 8 TMEM columns; sub-chunk j starts at column j*32
                                         ptx::umma_bf16_ts(d_tmem, tmem_base + j * (kChunkK / 2) + k * 8, db, idesc,
                                                           (j | k) != 0 ? 1u : 0u);
-                                    } else {       // hybrid q-tile: this K-chunk's A operand is in shared memory
+                                    } else {       // hybrid q-tile: this stage's A operand is in shared memory
                                         const uint64_t da = desc_hi | static_cast<uint64_t>(a_lo0 + (j - kQTmemChunks) * slab_lo + 2u * k);
                                         ptx::umma_bf16_ss(d_tmem, da, db, idesc, 1u);
                                     }
@@ -588,7 +581,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 // per-thread path, so q_bias_out is bit-identical.
                 // scratch: the list memory, which is not in use yet — or, beside a hybrid q-tile, the head of the q-tile's
                 // shared-memory half, which the producer fills only after this fill (bar_q)
-                uint8_t* scr = smem + (p.n_q_smem > 0 ? lay.q_off : lay.list_off) + (warp - 2) * 4096;
+                uint8_t* scr = smem + (kHybrid ? lay.q_off : lay.list_off) + (warp - 2) * 4096;
                 const void* s0 = kFuseQ ? p.qsrc0 : static_cast<const void*>(p.q);
                 const void* s1 = kFuseQ ? p.qsrc1 : nullptr;
                 const int sd0 = kFuseQ ? p.qd0 : p.d, sd1 = kFuseQ ? p.qd1 : 0;
@@ -666,10 +659,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                         }
                     }
                     ptx::tmem_st_32x32b_x32(q_taddr + c * (kChunkK / 2), w);
-                    ptx::tmem_wait_st();
-                    ptx::tc_fence_before();
                     __syncwarp();      // the scratch is rewritten by the next chunk
-                    if (lane == 0) ptx::mbar_arrive(bar_qc(c));
                 }
                 if constexpr (kFuseQ) {
                     if (split == 0 && p.q_bias_out) {                   // -0.5*|q|^2 for return_dists: the two halves meet here
@@ -682,7 +672,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                     ptx::named_bar_sync(4, 256);       // every warp is through with its scratch: the memory becomes lists
                     if (active_group) for (int i = 0; i < kk; ++i) my_list[i] = 0ull;
                 }
-                if (p.n_q_smem > 0) ptx::fence_proxy_async_smem();   // scratch accesses before the TMA that overwrites it
+                if constexpr (kHybrid) ptx::fence_proxy_async_smem();   // scratch accesses before the TMA that overwrites it
             } else if constexpr (kFuseQ) {
                 auto load_q8 = [&](int col, float (&x)[8]) {      // 8 consecutive elements of [src0 | src1]
                     if (col < p.qd0) load8(p.qsrc0, p.q_dtype, qrow_idx * p.qd0 + col, x);
