@@ -170,6 +170,9 @@ static int make_plan(mpr_context* h, int b, int64_t n_local, int d, int kk, Scan
             return (kMaxSmem - 1024 - static_cast<int>(fixed.total)) / kStageBytes;
         };
         pl->n_epi_groups = (!pl->reg_list && units_for(16, 2) < 6) ? 1 : 2;
+        // beside a full-height hybrid q-tile a fifth ring stage is worth more than the second epilogue group: a D = 1024
+        // tile streams for ~5 us, one group needs ~1.5 us of it
+        if (pl->hybrid && pl->q_box_rows > 64) pl->n_epi_groups = 1;
         if (h->epi_groups == 1 || (h->epi_groups == 2 && units_for(10, 2) >= 3)) pl->n_epi_groups = h->epi_groups;
         const int* caps = pl->reg_list ? caps0 : pl->n_epi_groups == 1 ? caps1 : caps2;
         const int n_caps = pl->reg_list ? 1 : pl->n_epi_groups == 1 ? 5 : 4;
