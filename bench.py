@@ -535,10 +535,17 @@ def run_native(args):
         ranks_agree = True
 
     if os.environ.get("MPR_DEBUG_COUNTERS"):
-        # tuning aid: per-CTA timeline of one more device step (see tools/probe_one.py for the event names); a sharded
-        # step is a collective, so every rank takes it and rank 0 reports
-        device_step()
+        # tuning aid: per-CTA timeline of the LAST of ten more back-to-back device steps (see tools/probe_one.py for the
+        # event names); a sharded step is a collective, so every rank takes them
         barrier()
+        for _ in range(10):
+            device_step()
+        barrier()
+    if os.environ.get("MPR_DEBUG_COUNTERS") and rank != 0:
+        tl = K.debug_timeline(K.search_plan(b, n_local, d, kk, dev.index)["n_ctas"], dev.index) / 1e3
+        sys.stderr.write(f"timeline rank {rank}: " + " ".join(
+            f"{nm}={np.median(tl[:, k_][tl[:, k_] >= 0]):.1f}" for k_, nm in
+            ((1, "q_ready"), (2, "producer_done"), (7, "cta_done"), (8, "past_barrier"), (9, "tail_done"))) + " us\n")
     if os.environ.get("MPR_DEBUG_COUNTERS") and rank == 0:
         tl = K.debug_timeline(K.search_plan(b, n_local, d, kk, dev.index)["n_ctas"], dev.index) / 1e3
         names = {1: "q_ready", 2: "producer_done", 7: "cta_done", 8: "past_grid_barrier", 9: "tail_done", 15: "tile0_ready",

@@ -48,6 +48,7 @@ struct mpr_context {
     int thr_rep_log2 = 2;                   // up to 4 replica words per threshold slot (MPR_THR_REPLICAS=1|2|4)
     int hybrid_min_b = 16;                  // ... for batches beyond this many queries (MPR_HYBRID_MIN_B)
     int use_hybrid = 1;                     // hybrid TMEM + shared-memory q-tile for 512 < D <= 1024 (MPR_NO_HYBRID=1 disables)
+    int xchg_mode = 0;                      // MPR_XCHG_MODE tuning bits (tail.cuh XchgParams::mode)
     int pdl = 0;                            // programmatic dependent launch of the scan kernel (MPR_PDL=1)
     int q_coop = 1;                         // warp-cooperative coalesced q-tile fill (MPR_NO_QCOOP=1: a thread per row)
     int tail_floor = 1;                     // pool merge drops keys below the final shared threshold (MPR_NO_TAIL_FLOOR=1)
@@ -423,6 +424,7 @@ static int run_step(mpr_context* h, const mpr_retrieve_args& a, float* dump, cud
     t.xchg.rank = a.world > 1 ? a.rank : 0;
     t.xchg.cap = a.xchg_cap;
     t.xchg.timeout_ns = h->xchg_timeout_ns;
+    t.xchg.mode = h->xchg_mode;
     if (a.world > 1)
         for (int r = 0; r < a.world; ++r) t.xchg.peers.buf[r] = static_cast<unsigned char*>(a.peer_bufs[r]);
     if (a.answer_id) {
@@ -581,6 +583,8 @@ int mpr_create(int device, mpr_handle_t* out) {
         if (flag("MPR_NO_TAIL_FLOOR")) h->tail_floor = 0;
         if (flag("MPR_NO_QCOOP")) h->q_coop = 0;
         if (flag("MPR_PDL")) h->pdl = 1;
+        const char* xm = getenv("MPR_XCHG_MODE");
+        if (xm) h->xchg_mode = atoi(xm);
         if (flag("MPR_NO_HYBRID")) h->use_hybrid = 0;
         const char* hb = getenv("MPR_HYBRID_MIN_B");
         if (hb && atoi(hb) >= 0) h->hybrid_min_b = atoi(hb);

@@ -210,6 +210,7 @@ struct XchgPeers {
 struct XchgParams {
     int world, rank, cap;          // world <= 1: no exchange
     unsigned long long timeout_ns; // how long a warp waits for a peer before it gives up (status = kErrXchgTimeout)
+    int mode;                      // tuning bits: 1 = system fence after the stores, 2 = poll with L2 (.cg) loads
     XchgPeers peers;               // peers.buf[rank] = this rank's own buffer
 };
 
@@ -269,6 +270,7 @@ __device__ __forceinline__ uint64_t warp_exchange(const XchgParams& x, uint32_t 
         for (int r = 0; r < x.world; ++r)
             st_relaxed_sys_v2_u64(reinterpret_cast<uint64_t*>(x.peers.buf[r] + kXchgDataOff) + off, w0, w1);
     }
+    if (x.mode & 1) __threadfence_system();
     const uint64_t* mine = reinterpret_cast<const uint64_t*>(x.peers.buf[x.rank] + kXchgDataOff) + parity_off;
     const int total = x.world * kk;
     uint64_t ent[kXchgMaxPerLane];
@@ -286,7 +288,13 @@ __device__ __forceinline__ uint64_t warp_exchange(const XchgParams& x, uint32_t 
             if (need & (1u << j)) {
                 const int idx = lane + 32 * j, r = idx / kk, i = idx - r * kk;
                 uint64_t a, b;
-                ld_relaxed_sys_v2_u64(mine + (static_cast<size_t>(r) * x.cap + static_cast<size_t>(q) * kk + i) * 2, a, b);
+                const uint64_t* src = mine + (static_cast<size_t>(r) * x.cap + static_cast<size_t>(q) * kk + i) * 2;
+                if (x.mode & 2) {
+                    const ulonglong2 v = __ldcg(reinterpret_cast<const ulonglong2*>(src));
+                    a = v.x; b = v.y;
+                } else {
+                    ld_relaxed_sys_v2_u64(src, a, b);
+                }
                 if ((a >> 32) == e && (b >> 32) == e) {
                     ent[j] = (b << 32) | (a & 0xFFFFFFFFull);
                     need &= ~(1u << j);
