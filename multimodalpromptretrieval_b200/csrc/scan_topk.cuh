@@ -57,7 +57,6 @@ constexpr int kCandCapMax = 16;               // per-query pending-candidate slo
 constexpr int kTileRing = 64;                 // scheduler -> consumers tile-id ring (entries); >= the producer's lead
 constexpr uint32_t kTileEnd = 0xFFFFFFFFu;
 constexpr int kQTmemChunks = 8;               // K-chunks of a q-tile that fit tensor memory (256 columns)
-constexpr int kMaxQChunkBars = 8;             // spare barrier slots
 
 struct ScanParams {
     int b_total;       // queries in the batch
@@ -130,7 +129,7 @@ __host__ __device__ inline ScanSmemLayout scan_smem_layout(int n_chunks /* of th
     l.ring_off = l.bias_off + kAccBufs * kTileRows * 4u;
     l.scr_off = l.ring_off + kTileRing * 8u;
     l.bar_off = l.scr_off + 2 * kUmmaM * 4u;
-    l.total = l.bar_off + (1 + 2 * kMaxStages + 2 * kAccBufs + kMaxQChunkBars + 1) * 8u + 16u;
+    l.total = l.bar_off + (2 + 2 * kMaxStages + 2 * kAccBufs) * 8u + 16u;
     return l;
 }
 
@@ -226,9 +225,9 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     auto bar_empty = [&](int s) { return bar_base + 8u + 8u * (kMaxStages + s); };
     auto bar_tfull = [&](int b) { return bar_base + 8u + 8u * (2 * kMaxStages + b); };
     auto bar_tempty = [&](int b) { return bar_base + 8u + 8u * (2 * kMaxStages + kAccBufs + b); };
-    const uint32_t bar_qs = bar_base + 8u + 8u * (2 * kMaxStages + 2 * kAccBufs + kMaxQChunkBars);   // hybrid q-tile: the shared-memory half has landed (TMA)
+    const uint32_t bar_qs = bar_base + 8u + 8u * (2 * kMaxStages + 2 * kAccBufs);   // hybrid q-tile: the shared-memory half has landed (TMA)
     volatile uint32_t* tmem_slot =
-        reinterpret_cast<volatile uint32_t*>(smem + lay.bar_off + (1 + 2 * kMaxStages + 2 * kAccBufs + kMaxQChunkBars + 1) * 8u);
+        reinterpret_cast<volatile uint32_t*>(smem + lay.bar_off + (2 + 2 * kMaxStages + 2 * kAccBufs) * 8u);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;

@@ -91,11 +91,36 @@ __device__ __forceinline__ uint64_t warp_merge_lists(const uint64_t* __restrict_
 // least kk keys reach, so everything below it is out; (2) the few survivors are inserted into the warp's sorted list.
 // Neither pass depends on the order inside the per-CTA lists, so the scan writes them unsorted, and unlike a rank-by-rank
 // walk over sorted lists there is no chain of dependent L2 round trips (14 us per query at k + skip = 32).
+// The scan's shared thresholds end as ns >= kk maxima over disjoint row sets: kk distinct rows score at least their
+// minimum, so a key whose score is strictly below it cannot be among the query's top kk (ties stay in).  `word` = this
+// lane's threshold word (word = slot * R + replica; lanes >= ns * R pass anything); returns the floor key or 0.
+__device__ __forceinline__ uint64_t floor_from_threshold_words(uint32_t word, int ns, int rep_log2, int lane) {
+    const int words = ns << rep_log2;
+    uint32_t mn = lane < words ? word : 0u;
+    if (rep_log2 >= 1) mn = max(mn, __shfl_xor_sync(kFullMask, mn, 1));      // maximum over a slot's replicas
+    if (rep_log2 >= 2) mn = max(mn, __shfl_xor_sync(kFullMask, mn, 2));
+    if (lane >= words) mn = 0xFFFFFFFFu;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mn = min(mn, __shfl_xor_sync(kFullMask, mn, o));
+    return mn > 0x00800000u ? (static_cast<uint64_t>(mn) << 32) - 1ull : 0ull;
+}
+
+// `thr_word`: where this lane's threshold word lives (nullptr = no floor from the thresholds); it is loaded AFTER the
+// pool's first round of loads has been issued, so both ride the same L2 round trip.  With a floor the pivot pass is
+// skipped for kk > 8, where the kk-th largest of 32 lane maxima is a weak pivot anyway.
 // `floor0`: a key known to lie below the pool's kk-th best (0 = none), e.g. from the scan's shared thresholds; with one
 // the pivot pass is skipped for kk > 8, where the kk-th largest of 32 lane maxima is a weak pivot anyway.
 template <bool kCoherent>
 __device__ __forceinline__ uint64_t warp_merge_pool(const uint64_t* __restrict__ pool, int m, int kk, int lane,
-                                                    uint64_t floor0 = 0ull) {
+                                                    const uint32_t* thr_word = nullptr, int ns = 0, int rep_log2 = 0) {
+    uint64_t key0[kMergeUnroll];      // the first round of loads goes out before anything else
+#pragma unroll
+    for (int u = 0; u < kMergeUnroll; ++u) {
+        const int i = u * 32 + lane;
+        key0[u] = i < m ? load_key<kCoherent>(pool + i) : 0ull;
+    }
+    uint64_t floor0 = 0ull;
+    if (thr_word) floor0 = floor_from_threshold_words(lane < (ns << rep_log2) ? __ldcg(thr_word) : 0u, ns, rep_log2, lane);
     uint64_t floor = floor0;
     const bool want_pivot = floor0 == 0ull || kk <= 8;
     auto pivot_of = [&](uint64_t lm) -> uint64_t {      // the kk-th largest of the 32 lane maxima, minus one
@@ -123,26 +148,22 @@ __device__ __forceinline__ uint64_t warp_merge_pool(const uint64_t* __restrict__
     if (m <= 32 * kMergeUnroll) {
         // the whole pool fits the warp's registers: ONE round of loads serves the pivot and the inserts (the headline
         // shape, 296 lists x 5 keys over ten warps, is 160 keys per warp)
-        uint64_t key[kMergeUnroll];
-#pragma unroll
-        for (int u = 0; u < kMergeUnroll; ++u) {
-            const int i = u * 32 + lane;
-            key[u] = i < m ? load_key<kCoherent>(pool + i) : 0ull;
-        }
         if (want_pivot) {
-            uint64_t lm = key[0];
+            uint64_t lm = key0[0];
 #pragma unroll
-            for (int u = 1; u < kMergeUnroll; ++u) lm = key[u] > lm ? key[u] : lm;
+            for (int u = 1; u < kMergeUnroll; ++u) lm = key0[u] > lm ? key0[u] : lm;
             const uint64_t pivot = pivot_of(lm);
             floor = pivot > floor ? pivot : floor;
         }
         uint64_t elem = 0ull, kth = floor;
-        insert_batch(key, elem, kth);
+        insert_batch(key0, elem, kth);
         return elem;
     }
     if (want_pivot) {
         uint64_t lm = 0ull;
-        for (int i0 = 0; i0 < m; i0 += 32 * kMergeUnroll) {
+#pragma unroll
+        for (int u = 0; u < kMergeUnroll; ++u) lm = key0[u] > lm ? key0[u] : lm;
+        for (int i0 = 32 * kMergeUnroll; i0 < m; i0 += 32 * kMergeUnroll) {
             uint64_t key[kMergeUnroll];
 #pragma unroll
             for (int u = 0; u < kMergeUnroll; ++u) {
@@ -156,7 +177,8 @@ __device__ __forceinline__ uint64_t warp_merge_pool(const uint64_t* __restrict__
         floor = pivot > floor ? pivot : floor;
     }
     uint64_t elem = 0ull, kth = floor;
-    for (int i0 = 0; i0 < m; i0 += 32 * kMergeUnroll) {
+    insert_batch(key0, elem, kth);
+    for (int i0 = 32 * kMergeUnroll; i0 < m; i0 += 32 * kMergeUnroll) {
         uint64_t key[kMergeUnroll];
 #pragma unroll
         for (int u = 0; u < kMergeUnroll; ++u) {
@@ -461,20 +483,9 @@ __device__ __forceinline__ void block_tail_query(const TailParams& t, int q, uin
     const uint64_t* pool = t.part_keys + static_cast<size_t>(q) * m;
     PromptPrefetch pf = {0, 0, 0, 0};
     if (warp == 0 && t.prompt.answer_id) pf = prompt_prefetch(t.prompt, q, lane);
-    // The scan's shared thresholds end as ns >= kk maxima over disjoint row sets: kk distinct rows score at least their
-    // minimum, so a key whose score is strictly below it cannot be among the query's top kk (ties stay in).
-    uint64_t floor0 = 0ull;
-    if (t.gthr && t.use_floor) {
-        const int words = t.ns << t.thr_rep_log2;          // word = slot * R + replica, <= 32
-        uint32_t mn = lane < words ? __ldcg(t.gthr + static_cast<size_t>(lane) * t.b + q) : 0u;
-        if (t.thr_rep_log2 >= 1) mn = max(mn, __shfl_xor_sync(kFullMask, mn, 1));      // maximum over a slot's replicas
-        if (t.thr_rep_log2 >= 2) mn = max(mn, __shfl_xor_sync(kFullMask, mn, 2));
-        if (lane >= words) mn = 0xFFFFFFFFu;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mn = min(mn, __shfl_xor_sync(kFullMask, mn, o));
-        if (mn > 0x00800000u) floor0 = (static_cast<uint64_t>(mn) << 32) - 1ull;
-    }
-    const uint64_t mine = warp_merge_pool<true>(pool + lo, hi - lo, t.kk, lane, floor0);
+    const uint32_t* thr_word = (t.gthr && t.use_floor) ? t.gthr + static_cast<size_t>(min(lane, (t.ns << t.thr_rep_log2) - 1)) * t.b + q
+                                                       : nullptr;
+    const uint64_t mine = warp_merge_pool<true>(pool + lo, hi - lo, t.kk, lane, thr_word, t.ns, t.thr_rep_log2);
     sbuf[warp * 32 + lane] = lane < t.kk ? mine : 0ull;
     __syncthreads();
     if (warp == 0) {
