@@ -367,8 +367,10 @@ def run_native(args):
     prefix_dev = (pre_ids.clone(), pre_off.clone(), longest)
 
     def device_step():
-        # inputs resident in HBM: one ctypes call, one launch (two for batches beyond one wave of CTAs)
-        return bank.run_step(q_dev, None, prefix_dev, True, False, kk=kk, skip=0)
+        # inputs resident in HBM: one ctypes call, one launch (two for batches beyond one wave of CTAs).  On a sharded bank
+        # the collection of the peers' candidates + vote + prompt ids of a step is a second, small kernel on the library's
+        # side stream (defer), so that the NVLink latency hides under the next step's scan; timed() joins it
+        return bank.run_step(q_dev, None, prefix_dev, True, False, kk=kk, skip=0, defer=world > 1)
 
     def barrier():
         if world > 1:
@@ -386,6 +388,8 @@ def run_native(args):
         e0.record()
         for _ in range(steps):
             fn()
+        if world > 1:
+            bank.join()          # every step's deferred finish is inside the timed region
         e1.record()
         barrier()
         t1 = time.time()

@@ -114,7 +114,8 @@ int mpr_merge_topk(mpr_handle_t h, const uint64_t* in_keys, int n_lists, int b, 
  * cap >= b*kk of any search that will use it.  The exchange itself runs inside mpr_retrieve (see there): per query, the
  * rank's merged local top-kk is stored into every peer's buffer as self-validating 8-byte words {half a key | epoch tag}
  * (plain P2P stores, no fence and no flag), the peers' words of the same query are polled in the rank's own buffer and
- * the `world` lists merged.  New in the build: the reference is single-device (main.py:58-61).
+ * the `world` lists merged — in the step kernel itself, or (defer_finish) in a small kernel on a side stream.  New in the
+ * build: the reference is single-device (main.py:58-61).
  */
 size_t mpr_exchange_bytes(int world, int cap);
 
@@ -192,11 +193,22 @@ typedef struct mpr_retrieve_args {
     int32_t* bucket;           /* [b] */
     int32_t* ret_answer;       /* [b][k] or NULL */
     int32_t* status;           /* device word, 0 = ok, MPR_STATUS_* otherwise (may be NULL) */
+    /* world > 1 only.  Non-zero: the step kernel only PUSHES this rank's candidates to the peers; collecting the peers'
+     * candidates, the merge, the vote and every output of the step are left to a small second kernel that the library
+     * queues on a stream of its own, so that the NVLink latency of the exchange (~10 us) hides under whatever follows
+     * on `stream` — normally the next step's scan.  The outputs are then NOT ordered before later work on `stream`:
+     * call mpr_retrieve_join(h, some_stream) before consuming them there (mpr_retrieve_host does it for its own
+     * device-to-host copy).  At most two deferred steps are left unfinished at any time (the library makes step j+2
+     * wait for the finish of step j).  Ignored for batches that take the two-launch path. */
+    int defer_finish;
 } mpr_retrieve_args;
 
 #define MPR_STATUS_XCHG_TIMEOUT 201 /* a peer rank did not deliver its candidates in time; local results returned */
 
 int mpr_retrieve(mpr_handle_t h, const mpr_retrieve_args* a, void* stream);
+
+/* Makes `stream` wait for every deferred finish (mpr_retrieve_args.defer_finish) queued so far on this handle. */
+int mpr_retrieve_join(mpr_handle_t h, void* stream);
 
 /*
  * The same step for HOST-resident inputs and outputs (what a data-loader thread hands over and what the T5 side of

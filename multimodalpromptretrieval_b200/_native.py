@@ -23,7 +23,7 @@ EXPORTS = [
     "mpr_search_workspace_bytes", "mpr_search_topk", "mpr_merge_topk", "mpr_prompt_gather", "mpr_debug_scores",
     "mpr_search_plan", "mpr_profile_begin", "mpr_profile_end", "mpr_profile_launch_ms", "mpr_exchange_bytes",
     "mpr_search_fused_supported", "mpr_search_topk_fused", "mpr_retrieve", "mpr_retrieve_host",
-    "mpr_set_exchange_timeout", "mpr_embed_prompt", "mpr_last_launch_count", "mpr_debug_counters", "mpr_debug_timeline", "mpr_debug_launch_ring", "mpr_workspace_invalidate",
+    "mpr_set_exchange_timeout", "mpr_embed_prompt", "mpr_last_launch_count", "mpr_debug_counters", "mpr_debug_timeline", "mpr_debug_launch_ring", "mpr_retrieve_join", "mpr_workspace_invalidate",
     "mpr_token_cache_create", "mpr_token_cache_destroy", "mpr_token_cache_size", "mpr_token_cache_clear",
     "mpr_token_cache_put", "mpr_token_cache_assemble",
 ]
@@ -45,6 +45,7 @@ class RetrieveArgs(C.Structure):
         ("out_stride", C.c_int),
         ("input_ids", C.c_void_p), ("attention_mask", C.c_void_p), ("out_len", C.c_void_p), ("maj_answer", C.c_void_p),
         ("maj_count", C.c_void_p), ("bucket", C.c_void_p), ("ret_answer", C.c_void_p), ("status", C.c_void_p),
+        ("defer_finish", C.c_int),
     ]
 
 
@@ -133,6 +134,8 @@ def load() -> C.CDLL:
                                              C.POINTER(i32)]
     lib.mpr_workspace_invalidate.restype = i32
     lib.mpr_workspace_invalidate.argtypes = [vp, vp]
+    lib.mpr_retrieve_join.restype = i32
+    lib.mpr_retrieve_join.argtypes = [vp, vp]
     lib.mpr_debug_launch_ring.restype = i32
     lib.mpr_debug_launch_ring.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint)]
     lib.mpr_debug_timeline.restype = i32

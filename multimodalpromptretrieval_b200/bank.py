@@ -200,7 +200,7 @@ class _Step:
         a.input_ids = base + self.head_bytes
         self._bound_base = base
 
-    def run(self, img, txt, prefix, use_quantifier: bool, to_host: bool) -> Dict[str, object]:
+    def run(self, img, txt, prefix, use_quantifier: bool, to_host: bool, defer: bool = False) -> Dict[str, object]:
         """``img`` / ``txt``: query halves, device tensors or (pinned) host tensors; ``prefix`` = None (vote only) or the
         host CSR ``(ids int32, off int32[b+1])`` of the per-query prefix tokens, or device tensors ``(ids, off, longest)``.
         Returns the result views (device; plus host views when ``to_host``, in which case the call has synchronised).
@@ -279,6 +279,10 @@ class _Step:
         else:
             io.d_out = io.h_out = 0
             io.out_bytes, io.sync = 0, 0
+        # sharded bank: leave the collection of the peers' candidates, the vote and the outputs to the finish kernel on
+        # the library's side stream (the NVLink latency then hides under the next step's scan).  Always for submitted
+        # steps (their result copy waits for the finish); on request otherwise (the caller joins: RetrievalBank.join)
+        a.defer_finish = 1 if (defer or to_host == "async") and a.world > 1 else 0
         copy_streams = bank._copy_streams() if to_host == "async" else None
         if copy_streams is not None:
             # Inputs on st_in, results on st_out.  The input copy overwrites this turn's device staging: the submitted
@@ -707,7 +711,8 @@ class RetrievalBank:
                              "kernel hold at most 32 candidates; the reference accepts any k")
 
     def run_step(self, img: torch.Tensor, txt: Optional[torch.Tensor] = None, prefix=None, use_quantifier: bool = True,
-                 to_host: bool = False, kk: Optional[int] = None, skip: Optional[int] = None) -> Dict[str, object]:
+                 to_host: bool = False, kk: Optional[int] = None, skip: Optional[int] = None, defer: bool = False
+                 ) -> Dict[str, object]:
         """One retrieval step on prepared inputs: query halves (device or host tensors) [+ prefix token CSR] ->
         top-(k+skip), vote, bucket [, prompt ids].  Returns {"device": views, "host": views (to_host), "stride"}; the
         views alias buffers that the step after next overwrites."""
@@ -722,7 +727,14 @@ class RetrievalBank:
         if self.exchange.world_size > 1 and self.exchange_mode == "nccl":
             return self._run_step_nccl(st, img, txt, prefix, use_quantifier, to_host)
         with torch.cuda.device(self.device), K.nvtx_range("mpr.retrieval_step"):
-            return st.run(img, txt, prefix, use_quantifier, to_host)
+            return st.run(img, txt, prefix, use_quantifier, to_host, defer)
+
+    def join(self) -> None:
+        """After ``run_step(..., defer=True)`` on a sharded bank: the current stream waits for the deferred part of every
+        step queued so far (collection of the peers' candidates, merge, vote, prompt ids), after which the device views
+        may be consumed on it."""
+        with torch.cuda.device(self.device):
+            K.retrieve_join(self.device)
 
     def _run_step_nccl(self, st: _Step, img, txt, prefix, use_quantifier, to_host) -> Dict[str, object]:
         """Sharded step with a collective library between two launches: local scan -> all-gather -> merge -> prompt."""

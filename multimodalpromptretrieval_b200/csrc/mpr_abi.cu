@@ -57,6 +57,13 @@ struct mpr_context {
     // first saw the pointer, every launch leaves them zero); most recently used last, at most 16
     std::vector<std::pair<const void*, size_t>> clean_ws;
     cudaEvent_t io_events[4] = {nullptr, nullptr, nullptr, nullptr};   // mpr_retrieve_host with copy streams
+    // deferred finish of sharded steps (mpr_retrieve_args.defer_finish): a stream of the library's own, per step j an
+    // event "scan j done" and an event "finish j done" (both indexed j & 3), and the epoch words the scan leaves behind
+    cudaStream_t fin_stream = nullptr;
+    cudaEvent_t fin_scan_done[4] = {nullptr, nullptr, nullptr, nullptr}, fin_done[4] = {nullptr, nullptr, nullptr, nullptr};
+    uint32_t* d_finish_epoch = nullptr;
+    unsigned fin_seq = 0;                   // deferred steps queued so far
+    bool last_deferred = false;             // the last run_step queued a deferred finish
     int io_turn = 0;
     unsigned launch_seq = 0;                // scan launches so far (debug ring index)
     int last_launches = 0;                  // kernel launches of the last mpr_retrieve
@@ -423,6 +430,26 @@ static int run_step(mpr_context* h, const mpr_retrieve_args& a, float* dump, cud
     t.xchg.world = a.world > 1 ? a.world : 1;
     t.xchg.rank = a.world > 1 ? a.rank : 0;
     t.xchg.cap = a.xchg_cap;
+    // deferred finish: only for sharded single-launch steps
+    const bool defer = !kDump && a.world > 1 && a.defer_finish && fused_tail;
+    h->last_deferred = false;
+    unsigned fin_j = 0;
+    if (defer) {
+        if (!h->fin_stream) {
+            CUDA_TRY(h, cudaStreamCreateWithFlags(&h->fin_stream, cudaStreamNonBlocking));
+            for (int i = 0; i < 4; ++i) {
+                CUDA_TRY(h, cudaEventCreateWithFlags(&h->fin_scan_done[i], cudaEventDisableTiming));
+                CUDA_TRY(h, cudaEventCreateWithFlags(&h->fin_done[i], cudaEventDisableTiming));
+            }
+            CUDA_TRY(h, cudaMalloc(&h->d_finish_epoch, 4 * sizeof(uint32_t)));
+            CUDA_TRY(h, cudaMemset(h->d_finish_epoch, 0, 4 * sizeof(uint32_t)));
+        }
+        fin_j = h->fin_seq++;
+        // step j is queued only after the finish of step j-2 has run (bounds what is in flight; see tail.cuh)
+        if (fin_j >= 2) CUDA_TRY(h, cudaStreamWaitEvent(st, h->fin_done[(fin_j - 2) & 3], 0));
+        t.defer_xchg = 1;
+        t.finish_epoch = h->d_finish_epoch + (fin_j & 3);
+    }
     t.xchg.timeout_ns = h->xchg_timeout_ns;
     t.xchg.mode = h->xchg_mode;
     if (a.world > 1)
@@ -478,6 +505,15 @@ static int run_step(mpr_context* h, const mpr_retrieve_args& a, float* dump, cud
         tail_kernel<<<blocks, kTailWarps * 32, 0, st>>>(t);
         CUDA_TRY(h, cudaGetLastError());
         ++h->last_launches;
+    }
+    if (defer) {
+        CUDA_TRY(h, cudaEventRecord(h->fin_scan_done[fin_j & 3], st));
+        CUDA_TRY(h, cudaStreamWaitEvent(h->fin_stream, h->fin_scan_done[fin_j & 3], 0));
+        xchg_finish_kernel<<<(b + kFinishWarps - 1) / kFinishWarps, kFinishWarps * 32, 0, h->fin_stream>>>(t);
+        CUDA_TRY(h, cudaGetLastError());
+        CUDA_TRY(h, cudaEventRecord(h->fin_done[fin_j & 3], h->fin_stream));
+        ++h->last_launches;
+        h->last_deferred = true;
     }
     return MPR_OK;
 }
@@ -658,6 +694,10 @@ int mpr_destroy(mpr_handle_t h) {
     DeviceGuard guard(h->device);
     for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
     for (cudaEvent_t e : h->io_events) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->fin_scan_done) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->fin_done) if (e) cudaEventDestroy(e);
+    if (h->fin_stream) cudaStreamDestroy(h->fin_stream);
+    if (h->d_finish_epoch) cudaFree(h->d_finish_epoch);
     if (h->d_err) cudaFree(h->d_err);
     if (h->d_dbg) cudaFree(h->d_dbg);
     delete h;
@@ -780,6 +820,14 @@ int mpr_retrieve(mpr_handle_t h, const mpr_retrieve_args* a, void* stream) {
     return run_step<false>(h, *a, nullptr, static_cast<cudaStream_t>(stream));
 }
 
+int mpr_retrieve_join(mpr_handle_t h, void* stream) {
+    if (!h) return fail(nullptr, MPR_EINVAL, "null handle");
+    if (h->fin_seq == 0) return MPR_OK;
+    DeviceGuard guard(h->device);
+    CUDA_TRY(h, cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), h->fin_done[(h->fin_seq - 1) & 3], 0));
+    return MPR_OK;
+}
+
 int mpr_retrieve_host(mpr_handle_t h, const mpr_retrieve_args* a, const mpr_host_io* io, void* stream) {
     if (!h) return fail(nullptr, MPR_EINVAL, "null handle");
     if (!io) return fail(h, MPR_EINVAL, "null io block");
@@ -826,7 +874,9 @@ int mpr_retrieve_host(mpr_handle_t h, const mpr_retrieve_args* a, const mpr_host
     rc = run_step<false>(h, *a, nullptr, st);
     if (rc) return rc;
     if (io->h_out && io->d_out && io->out_bytes) {
-        if (st_out != st) {
+        if (h->last_deferred) {        // the step's outputs come from the finish kernel on the library's stream
+            CUDA_TRY(h, cudaStreamWaitEvent(st_out, h->fin_done[(h->fin_seq - 1) & 3], 0));
+        } else if (st_out != st) {
             CUDA_TRY(h, cudaEventRecord(ev_step, st));
             CUDA_TRY(h, cudaStreamWaitEvent(st_out, ev_step, 0));
         }

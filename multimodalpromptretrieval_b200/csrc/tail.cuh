@@ -205,8 +205,8 @@ __device__ __forceinline__ void store_merged(uint64_t elem, int q, int kk, int l
 //
 //   byte 0      u32 epoch                  last exchange this rank has fully consumed
 //   byte 4      u32 done                   tail tickets of the launch in flight (stand-alone tail kernel only)
-//   byte 1024   u64 word[2][world][cap][2] candidate lists ([q][kk] keys inside a [rank] block, two words per key),
-//                                          double-buffered on epoch parity
+//   byte 1024   u64 word[4][world][cap][2] candidate lists ([q][kk] keys inside a [rank] block, two words per key),
+//                                          four buffers used in turn (exchange e uses buffer e & 3)
 //
 // Exchange e = epoch + 1.  A key travels as TWO self-validating 8-byte words, {low half | e << 32} and
 // {high half | e << 32}: an aligned 8-byte store is single-copy atomic, so a reader that finds tag e in a word has that
@@ -216,12 +216,17 @@ __device__ __forceinline__ void store_merged(uint64_t elem, int q, int kk, int l
 // OWN buffer until every word carries tag e and merges the world lists (keys are unique — they embed the global row — so
 // the merge is order-independent and ties still resolve to the lower row).  The last warp of the launch publishes
 // epoch = e.  Stale words carry an older tag (or 0) whatever batch shape wrote them.
-// Why two parities are enough: a rank can start exchange e+1 (writing word[(e+1)&1]) while a slow peer still reads
-// word[e&1], but it cannot reach e+2 before that peer has delivered its own e+1 words, which it does only after its
-// merge of e.  The waiting warp only ever waits on OTHER GPUs, never on a kernel that must be co-scheduled on its own.
+// Why four buffers are enough.  In-kernel collection: a rank can start exchange e+1 while a slow peer still reads the
+// words of e, but it cannot reach e+2 before that peer has delivered its own e+1 words, which it does only after its
+// merge of e (two buffers would do).  DEFERRED collection (the step kernel only pushes; `xchg_finish_kernel` on a side
+// stream collects, so that the NVLink latency hides under the next step's scan): the host lets step j+2 be queued only
+// after the finish of step j has run on this rank, so a rank reaching the push of e+4 has finished e+2, hence holds
+// every peer's words of e+2, hence every peer has launched e+2, hence finished e — nobody still reads buffer e & 3.
+// The waiting warp only ever waits on OTHER GPUs, never on a kernel that must be co-scheduled on its own.
 // Sharded search is therefore a COLLECTIVE call: every rank must issue the same sequence of searches.
 constexpr int kXchgMaxWorld = 16;
 constexpr int kXchgDataOff = 1024;
+constexpr int kXchgBuffers = 4;
 constexpr int kXchgMaxPerLane = kXchgMaxWorld * 32 / 32;      // world * kk <= 512 keys, spread over 32 lanes
 constexpr int kErrXchgTimeout = 201;
 
@@ -237,7 +242,7 @@ struct XchgParams {
 };
 
 __host__ __device__ inline size_t xchg_bytes(int world, int cap) {
-    return static_cast<size_t>(kXchgDataOff) + 2ull * world * cap * 2ull * sizeof(uint64_t);
+    return static_cast<size_t>(kXchgDataOff) + static_cast<size_t>(kXchgBuffers) * world * cap * 2ull * sizeof(uint64_t);
 }
 
 __device__ __forceinline__ void st_relaxed_sys_v2_u64(uint64_t* p, uint64_t a, uint64_t b) {
@@ -280,20 +285,25 @@ __device__ __forceinline__ uint64_t warp_merge_regs(const uint64_t (&key)[kN], i
     return elem;
 }
 
-// Exchange of one query's merged local list (`elem`, one element per lane) with all ranks; returns the global list.
-// `e` is the exchange epoch of this launch.  On a timeout *status receives kErrXchgTimeout and the LOCAL list is returned.
-__device__ __forceinline__ uint64_t warp_exchange(const XchgParams& x, uint32_t e, uint64_t elem, int q, int kk, int lane,
-                                                  int* status) {
+// Push of one query's merged local list (`elem`, one element per lane) into every rank's buffer (own included).
+__device__ __forceinline__ void warp_exchange_push(const XchgParams& x, uint32_t e, uint64_t elem, int q, int kk, int lane) {
     const uint64_t tag = static_cast<uint64_t>(e) << 32;
-    const size_t parity_off = static_cast<size_t>(e & 1u) * x.world * x.cap * 2;      // in words
+    const size_t buf_off = static_cast<size_t>(e & (kXchgBuffers - 1)) * x.world * x.cap * 2;      // in words
     if (lane < kk) {
         const uint64_t w0 = (elem & 0xFFFFFFFFull) | tag, w1 = (elem >> 32) | tag;
-        const size_t off = parity_off + (static_cast<size_t>(x.rank) * x.cap + static_cast<size_t>(q) * kk + lane) * 2;
+        const size_t off = buf_off + (static_cast<size_t>(x.rank) * x.cap + static_cast<size_t>(q) * kk + lane) * 2;
         for (int r = 0; r < x.world; ++r)
             st_relaxed_sys_v2_u64(reinterpret_cast<uint64_t*>(x.peers.buf[r] + kXchgDataOff) + off, w0, w1);
     }
     if (x.mode & 1) __threadfence_system();
-    const uint64_t* mine = reinterpret_cast<const uint64_t*>(x.peers.buf[x.rank] + kXchgDataOff) + parity_off;
+}
+
+// Collection of one query's lists from all ranks out of this rank's own buffer; returns the global list.  On a timeout
+// *status receives kErrXchgTimeout, *timed_out is set and whatever has arrived (the own list at least) is merged.
+__device__ __forceinline__ uint64_t warp_exchange_collect(const XchgParams& x, uint32_t e, int q, int kk, int lane,
+                                                          int* status, bool* timed_out) {
+    const size_t buf_off = static_cast<size_t>(e & (kXchgBuffers - 1)) * x.world * x.cap * 2;      // in words
+    const uint64_t* mine = reinterpret_cast<const uint64_t*>(x.peers.buf[x.rank] + kXchgDataOff) + buf_off;
     const int total = x.world * kk;
     uint64_t ent[kXchgMaxPerLane];
     unsigned need = 0u;
@@ -304,6 +314,7 @@ __device__ __forceinline__ uint64_t warp_exchange(const XchgParams& x, uint32_t 
     }
     const uint64_t t0 = ptx::globaltimer_ns();
     bool ok = true;
+    *timed_out = false;
     for (uint32_t polls = 0;; ++polls) {
 #pragma unroll
         for (int j = 0; j < kXchgMaxPerLane; ++j) {
@@ -327,10 +338,21 @@ __device__ __forceinline__ uint64_t warp_exchange(const XchgParams& x, uint32_t 
         if ((polls & 0x3Fu) == 0x3Fu && ptx::globaltimer_ns() - t0 > x.timeout_ns) ok = false;
         if (!__all_sync(kFullMask, ok)) {
             if (lane == 0 && status) atomicMax(status, kErrXchgTimeout);
-            return elem;
+            *timed_out = true;
+            break;
         }
     }
     return warp_merge_regs<kXchgMaxPerLane>(ent, kk, lane);
+}
+
+// Exchange of one query's merged local list with all ranks inside one kernel; returns the global list, or — when a
+// peer did not deliver in time (status = kErrXchgTimeout) — the LOCAL list.
+__device__ __forceinline__ uint64_t warp_exchange(const XchgParams& x, uint32_t e, uint64_t elem, int q, int kk, int lane,
+                                                  int* status) {
+    warp_exchange_push(x, e, elem, q, kk, lane);
+    bool timed_out;
+    const uint64_t merged = warp_exchange_collect(x, e, q, kk, lane, status, &timed_out);
+    return timed_out ? elem : merged;
 }
 
 // ------------------------------------------------------------------------------------------------ vote + prompt ids
@@ -467,6 +489,8 @@ struct TailParams {
     float* out_score;
     int32_t* out_idx;
     int* status;                 // device word: 0 = ok (may be nullptr)
+    int defer_xchg;              // world > 1: push only; xchg_finish_kernel (side stream) collects, votes and writes the outputs
+    uint32_t* finish_epoch;      // deferred: the launch's last ticket leaves its exchange epoch here for the finish kernel
     XchgParams xchg;
     PromptParams prompt;
 };
@@ -482,7 +506,7 @@ __device__ __forceinline__ void block_tail_query(const TailParams& t, int q, uin
     const int lo = min(m, warp * per), hi = min(m, lo + per);
     const uint64_t* pool = t.part_keys + static_cast<size_t>(q) * m;
     PromptPrefetch pf = {0, 0, 0, 0};
-    if (warp == 0 && t.prompt.answer_id) pf = prompt_prefetch(t.prompt, q, lane);
+    if (warp == 0 && t.prompt.answer_id && !(t.xchg.world > 1 && t.defer_xchg)) pf = prompt_prefetch(t.prompt, q, lane);
     const uint32_t* thr_word = (t.gthr && t.use_floor) ? t.gthr + static_cast<size_t>(min(lane, (t.ns << t.thr_rep_log2) - 1)) * t.b + q
                                                        : nullptr;
     const uint64_t mine = warp_merge_pool<true>(pool + lo, hi - lo, t.kk, lane, thr_word, t.ns, t.thr_rep_log2);
@@ -491,12 +515,16 @@ __device__ __forceinline__ void block_tail_query(const TailParams& t, int q, uin
     if (warp == 0) {
         uint64_t elem = warp_merge_lists<false>(sbuf, kWarps, 32ll, 1ll, t.kk, lane);
         if (t.gthr && lane < (t.ns << t.thr_rep_log2)) t.gthr[static_cast<size_t>(lane) * t.b + q] = 0u;     // leave the thresholds zeroed
+        if (t.xchg.world > 1 && t.defer_xchg) {
+            warp_exchange_push(t.xchg, e, elem, q, t.kk, lane);      // the rest of the query happens in xchg_finish_kernel
+        } else {
         if (t.xchg.world > 1) elem = warp_exchange(t.xchg, e, elem, q, t.kk, lane, t.status);
         store_merged(elem, q, t.kk, lane, t.out_keys, t.out_score, t.out_idx);
         if (t.prompt.answer_id) {
             const uint64_t src = shfl_u64(elem, min(lane + t.prompt.skip, 31));
             const int row = (lane < t.kk - t.prompt.skip) ? key_row(src) : -1;
             warp_vote_and_gather(t.prompt, q, row, lane, pf);
+        }
         }
     }
     __syncthreads();
@@ -512,6 +540,7 @@ __device__ __forceinline__ void tail_ticket(const TailParams& t, uint32_t e, uin
         t.ctrl[0] = 0u;
         t.ctrl[1] = 0u;
         if (t.xchg.world > 1) {
+            if (t.defer_xchg && t.finish_epoch) *t.finish_epoch = e;
             __threadfence();
             *reinterpret_cast<volatile uint32_t*>(t.xchg.peers.buf[t.xchg.rank]) = e;
         }
@@ -528,6 +557,31 @@ __global__ void __launch_bounds__(kTailWarps * 32) tail_kernel(const TailParams 
     if (t.xchg.world > 1) e = *reinterpret_cast<volatile uint32_t*>(t.xchg.peers.buf[t.xchg.rank]) + 1u;
     for (int q = blockIdx.x; q < t.b; q += gridDim.x) block_tail_query<kTailWarps>(t, q, e, sbuf, warp, lane);
     if (threadIdx.x == 0) tail_ticket(t, e, gridDim.x);
+}
+
+// Deferred half of a sharded step (TailParams::defer_xchg): one warp per query collects the ranks' lists from this
+// rank's exchange buffer — by the time it runs, on a side stream next to the NEXT step's scan, they have normally all
+// arrived — merges them, writes the search outputs, votes and gathers the prompt ids.
+// One warp per block and few registers: it has to fit NEXT TO a resident step CTA (10 warps x 168 registers leave
+// 256 registers free on two of an SM's four register-file partitions and 5.6 K on the other two; a 4-warp block, one
+// warp per partition, never fits and would only run once the next step's kernel has left).
+constexpr int kFinishWarps = 1;
+
+__global__ void __maxnreg__(64) xchg_finish_kernel(const TailParams t) {
+    const int lane = threadIdx.x & 31;
+    const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (q >= t.b) return;
+    const uint32_t e = *reinterpret_cast<volatile const uint32_t*>(t.finish_epoch);
+    PromptPrefetch pf = {0, 0, 0, 0};
+    if (t.prompt.answer_id) pf = prompt_prefetch(t.prompt, q, lane);
+    bool timed_out;
+    const uint64_t elem = warp_exchange_collect(t.xchg, e, q, t.kk, lane, t.status, &timed_out);
+    store_merged(elem, q, t.kk, lane, t.out_keys, t.out_score, t.out_idx);
+    if (t.prompt.answer_id) {
+        const uint64_t src = shfl_u64(elem, min(lane + t.prompt.skip, 31));
+        const int row = (lane < t.kk - t.prompt.skip) ? key_row(src) : -1;
+        warp_vote_and_gather(t.prompt, q, row, lane, pf);
+    }
 }
 
 }  // namespace mpr

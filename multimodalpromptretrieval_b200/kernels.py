@@ -274,6 +274,12 @@ def retrieve(args: "_native.RetrieveArgs", device: torch.device, io: Optional["_
         h.check(h.lib.mpr_retrieve_host(h.ptr, C.byref(args), C.byref(io), _stream(device)), "mpr_retrieve_host")
 
 
+def retrieve_join(device: torch.device) -> None:
+    """Makes the current stream wait for every deferred finish queued so far (``RetrieveArgs.defer_finish``)."""
+    h = handle(device.index)
+    h.check(h.lib.mpr_retrieve_join(h.ptr, _stream(device)), "mpr_retrieve_join")
+
+
 def debug_counters(device: Optional[int] = None) -> dict:
     """Scan-kernel event counters since the last call (all zero unless MPR_DEBUG_COUNTERS=1 was set at handle creation)."""
     h = handle(device)

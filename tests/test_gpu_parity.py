@@ -462,13 +462,14 @@ def K_handle_ok():
     return kernels.handle(0).device_error() == 0
 
 
-@pytest.mark.parametrize("world,b", [(2, 37), (8, 37), (8, 300), (2, 300)])
-def test_p2p_exchange_protocol_on_one_gpu(K, world, b):
+@pytest.mark.parametrize("world,b,defer", [(2, 37, 0), (8, 37, 0), (8, 300, 0), (2, 300, 0), (2, 37, 1), (8, 128, 1)])
+def test_p2p_exchange_protocol_on_one_gpu(K, world, b, defer):
     """The peer-memory exchange of the retrieval tail (csrc/tail.cuh) with the OTHER ranks' deliveries pre-populated in
     the exchange buffer (nothing here ever waits on a kernel that has not finished): rank r of `world` scans its shard,
     pushes its lists, finds every peer's tagged words already in place and merges — the result must equal the unsharded search,
     bit for bit, over several epochs (both slot parities).  (world 2, b 300) is more than one wave of CTAs and takes the
-    two-launch path (stand-alone tail kernel)."""
+    two-launch path (stand-alone tail kernel).  defer = 1: the step kernel only pushes, the finish kernel on the
+    library's side stream collects, merges and writes the outputs (mpr_retrieve_join orders them before the checks)."""
     from multimodalpromptretrieval_b200 import _native
     from multimodalpromptretrieval_b200.sharding import P2PExchange, shard_bounds
     import ctypes as C
@@ -482,7 +483,7 @@ def test_p2p_exchange_protocol_on_one_gpu(K, world, b):
     x = P2PExchange(dev(), cap, world_size=world, rank=me)
     nbytes = K.exchange_bytes(world, cap)
     data_off = 1024
-    assert nbytes == data_off + 2 * world * cap * 16          # two tagged 8-byte words per key, two parities
+    assert nbytes == data_off + 4 * world * cap * 16          # two tagged 8-byte words per key, four buffers in turn
     b0, b1 = shard_bounds(n, me, world)
     shard, sbias = bd[b0:b1].contiguous(), bias[b0:b1].contiguous()
     status = torch.zeros(4, dtype=torch.int32, device=dev())
@@ -495,9 +496,9 @@ def test_p2p_exchange_protocol_on_one_gpu(K, world, b):
         out_idx = torch.empty((b, kk), dtype=torch.int32, device=dev())
         q = torch.cat([bank[:b // 2].clone(), clip_like(b - b // 2, d, 40 + epoch)]).to(dev())
         full_keys, _, full_idx = K.search_topk(q, bd, bias, kk)
-        # what the peers would have delivered: their shard's lists into word[epoch & 1][r] as {key half | epoch << 32}
+        # what the peers would have delivered: their shard's lists into word[epoch & 3][r] as {key half | epoch << 32}
         host = x.buf.cpu().numpy().copy()
-        words = host[data_off:].view(np.uint64).reshape(2, world, cap, 2)
+        words = host[data_off:].view(np.uint64).reshape(4, world, cap, 2)
         for r in range(world):
             if r == me:
                 continue
@@ -505,8 +506,8 @@ def test_p2p_exchange_protocol_on_one_gpu(K, world, b):
             k_r, _, _ = K.search_topk(q, bd[r0:r1].contiguous(), bias[r0:r1].contiguous(), kk, idx_base=r0)
             keys = k_r.cpu().numpy().view(np.uint64).reshape(-1)
             tag = np.uint64(epoch) << np.uint64(32)
-            words[epoch & 1, r, :b * kk, 0] = (keys & np.uint64(0xFFFFFFFF)) | tag
-            words[epoch & 1, r, :b * kk, 1] = (keys >> np.uint64(32)) | tag
+            words[epoch & 3, r, :b * kk, 0] = (keys & np.uint64(0xFFFFFFFF)) | tag
+            words[epoch & 3, r, :b * kk, 1] = (keys >> np.uint64(32)) | tag
         x.buf.copy_(torch.from_numpy(host))
         a = _native.RetrieveArgs()
         a.q_bf16, a.b, a.bank, a.bias = q.data_ptr(), b, shard.data_ptr(), sbias.data_ptr()
@@ -514,8 +515,14 @@ def test_p2p_exchange_protocol_on_one_gpu(K, world, b):
         a.out_keys, a.out_idx, a.status = out_keys.data_ptr(), out_idx.data_ptr(), status.data_ptr()
         a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
         x.fill_args(a)
+        a.defer_finish = defer
         K.retrieve(a, dev())
-        assert K.last_launch_count() == (1 if K.search_plan(b, b1 - b0, d, kk)["n_ctas"] <= 148 else 2)
+        if defer:
+            assert K.last_launch_count() == 2                              # step kernel + finish kernel
+            K.retrieve_join(dev())
+            torch.cuda.synchronize()
+        else:
+            assert K.last_launch_count() == (1 if K.search_plan(b, b1 - b0, d, kk)["n_ctas"] <= 148 else 2)
         if (world, b) == (2, 300):
             assert K.last_launch_count() == 2
         if epoch == 4:

@@ -54,7 +54,7 @@ full, _, _ = K.search_topk(q, bank, bias, kk)
 x = P2PExchange(dev, cap, world_size=2, rank=0)
 other, _, _ = K.search_topk(q, bank[n // 2:].contiguous(), bias[n // 2:].contiguous(), kk, idx_base=n // 2)
 host = x.buf.cpu().numpy().copy()
-words = host[1024:].view(np.uint64).reshape(2, 2, cap, 2)        # [parity][rank][key][half], tagged with the epoch (1)
+words = host[1024:].view(np.uint64).reshape(4, 2, cap, 2)        # [parity][rank][key][half], tagged with the epoch (1)
 okeys = other.cpu().numpy().view(np.uint64).reshape(-1)
 tag = np.uint64(1) << np.uint64(32)
 words[1, 1, :b * kk, 0] = (okeys & np.uint64(0xFFFFFFFF)) | tag
