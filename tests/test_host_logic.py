@@ -171,6 +171,36 @@ def test_header_is_plain_c():
     assert res.returncode == 0, res.stderr
 
 
+def test_ctypes_mirrors_match_the_header_structs(tmp_path):
+    """``_native.RetrieveArgs`` / ``HostIO`` are written by hand next to ``mpr_retrieve_args`` / ``mpr_host_io``: size and
+    every field offset must agree with what a C compiler makes of include/mpr_b200.h."""
+    import shutil
+    import subprocess
+    from multimodalpromptretrieval_b200 import _native
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    pairs = [("mpr_retrieve_args", _native.RetrieveArgs), ("mpr_host_io", _native.HostIO)]
+    lines = ['#include <stddef.h>', '#include <stdio.h>', '#include "%s"' % os.path.join(ROOT, "include", "mpr_b200.h"),
+             "int main(void) {"]
+    for cname, cls in pairs:
+        lines.append('printf("%%zu\\n", sizeof(%s));' % cname)
+        for fname, _ in cls._fields_:
+            lines.append('printf("%%zu\\n", offsetof(%s, %s));' % (cname, fname))
+    lines.append("return 0; }")
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    res = subprocess.run([gcc, "-std=c99", "-o", str(exe), str(src)], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True).stdout.split()]
+    want = []
+    for _, cls in pairs:
+        want.append(ctypes.sizeof(cls))
+        want.extend(getattr(cls, fname).offset for fname, _ in cls._fields_)
+    assert got == want
+
+
 def test_word_cached_tokenisation_equals_direct_tokenisation(tokenizer):
     """encode_by_words (per-chunk cache) == the tokenizer on the whole string, cold and warm, incl. odd whitespace,
     punctuation-only chunks and non-ASCII text (which must take the direct path)."""
