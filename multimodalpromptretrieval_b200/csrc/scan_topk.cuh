@@ -16,11 +16,13 @@
 // CTAs resident at the same time walk the bank together and all but the first read of a tile hit L2.
 //
 // Shared admission thresholds: every (CTA, epilogue group) list publishes its best score with atomicMax into one of
-// ns >= kk slots per query (slot = list id mod ns).  The lists cover disjoint rows, so the MINIMUM over a query's ns
-// slots is a lower bound on its global kk-th best score: ns distinct rows are known to score at least that much, and
-// anything strictly below it can be dropped by every CTA without ever entering a list.  After the first tile this
-// replaces each CTA's slowly converging private threshold (k-th best of ITS rows) by a near-global one, which is what
-// keeps list maintenance off the critical path for large k and for small per-GPU shards.
+// ns >= kk slots per query.  The lists cover disjoint rows, so the MINIMUM over a query's ns slots is a lower bound on
+// its global kk-th best score: ns distinct rows are known to score at least that much, and anything strictly below it
+// can be dropped by every CTA without ever entering a list.  This replaces each CTA's slowly converging private
+// threshold (k-th best of ITS rows) by a near-global one, which is what keeps list maintenance off the critical path
+// for large k and for small per-GPU shards.  A list's FIRST tile is walked twice: pass 1 only publishes the tile's
+// maximum, then the warp waits (bounded) for every slot of its queries to be filled, and pass 2 admits against that
+// bound — a blind first tile cost 15 us (k = 5) to 30 us (k + skip = 32) per launch.
 //
 // Warp roles (320 threads): warp 0 = TMA producer + tile scheduler, warp 1 = TMEM allocator + MMA issuer (one elected
 // lane), warps 2..9 = two epilogue groups of four warps (warp w reads TMEM lanes 32*(w%4)...); group g takes this CTA's
