@@ -132,7 +132,7 @@ class ClockSampler:
     region of a `--steps 20` run is ~30 ms — shorter than one period of `nvidia-smi -lms`); falls back to nvidia-smi."""
     REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
-    def __init__(self, gpu_index: int, period_ms: int = 4):
+    def __init__(self, gpu_index: int, period_ms: int = 2):
         self.samples, self.thread, self.proc, self._stop = [], None, None, False
         self.sm_max = None
         try:
@@ -190,6 +190,12 @@ class ClockSampler:
     def window(self, t0: float, t1: float):
         """Summary of the samples taken between t0 and t1 (the sampler keeps running)."""
         rows = [s_ for s_ in self.samples if t0 <= s_[0] <= t1 + 0.002]
+        nearest = False
+        if not rows:
+            # a region shorter than one polling period (20 steps of 0.2 ms at 8 GPUs): the samples that bracket it
+            before = [s_ for s_ in self.samples if t0 - 0.02 <= s_[0] < t0][-1:]
+            after = [s_ for s_ in self.samples if t1 < s_[0] <= t1 + 0.02][:1]
+            rows, nearest = before + after, True
         if not rows:
             return None
         sm = sorted(r[1] for r in rows)
@@ -198,7 +204,8 @@ class ClockSampler:
             bits |= r[3]
         return {"sm_mhz": sm[len(sm) // 2], "sm_mhz_min": sm[0], "sm_max_mhz": self.sm_max,
                 "reasons": [n for n, m in self.REASONS.items() if bits & m],
-                "power_w_max": max(r[2] for r in rows), "samples": len(rows)}
+                "power_w_max": max(r[2] for r in rows), "samples": len(rows),
+                **({"note": "no sample inside the region; these bracket it within 20 ms"} if nearest else {})}
 
     def stop(self):
         self._stop = True
@@ -589,6 +596,12 @@ def run_native(args):
             "roofline": roofline,
             "plan": K.search_plan(b, n_local, d, kk, dev.index),
             "exchange": args.exchange if world > 1 else None,
+            "deferred_finish": (world > 1 and args.exchange == "p2p") or None,
+            "deferred_finish_note": ("value / roofline steps: the step kernel pushes this rank's candidates to the peers; a "
+                                     "one-warp-per-query finish kernel on the library's side stream collects them, votes and "
+                                     "writes the outputs next to the following step's scan (2 launches per step, every finish "
+                                     "joined inside the timed region).  e2e steps keep the exchange inside the step kernel"
+                                     ) if world > 1 and args.exchange == "p2p" else None,
             "result_digest": digest, "result_digest_key": dkey, "result_digest_expected": expected,
             "result_digest_matches_n1": (digest == expected) if expected else None, "ranks_agree": ranks_agree,
             "sample_output": {"prompt_tokens": int(dv["length"].max().item()),
