@@ -207,6 +207,13 @@ class ClockSampler:
                 "power_w_max": max(r[2] for r in rows), "samples": len(rows),
                 **({"note": "no sample inside the region; these bracket it within 20 ms"} if nearest else {})}
 
+    def wait_ready(self, timeout_s: float = 3.0) -> None:
+        """Blocks until the first sample is in (NVML start-up takes tens of milliseconds — longer than a whole timed
+        region at 8 GPUs)."""
+        t_end = time.time() + timeout_s
+        while not self.samples and time.time() < t_end:
+            time.sleep(0.005)
+
     def stop(self):
         self._stop = True
         if self.proc is not None:
@@ -416,6 +423,8 @@ def run_native(args):
     digest = {"rows": zlib.crc32(dv["idx"].cpu().numpy().tobytes()),
               "prompt_ids": zlib.crc32(dv["input_ids"].cpu().numpy().tobytes())}
     sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.wait_ready()
     warm = max(args.warmup, 3)
     # THE timed region: W warm-up steps, then exactly K steps; every launch of it is also bracketed by cudaEvents on its
     # stream (mpr_profile_begin/end) so that the roofline speaks about the same K steps as `value`
