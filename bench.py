@@ -517,8 +517,9 @@ def run_native(args):
     if os.path.exists(tpath):
         try:
             tj = json.load(open(tpath))
-            if tj.get("rows_per_gpu") == n_local and tj.get("batch") == b and tj.get("dim", 512) == d:
-                traffic = tj.get("dram_bytes_per_launch")
+            for ent in [tj] + list(tj.get("entries", [])):        # one capture per profiled shard size
+                if ent.get("rows_per_gpu") == n_local and ent.get("batch") == b and ent.get("dim", 512) == d:
+                    traffic = ent.get("dram_bytes_per_launch")
         except Exception:
             pass
     per_launch = flops / 1e12 if bound == "tensor" else alg_bytes / 1e9
