@@ -327,6 +327,16 @@ int mpr_profile_launch_ms(mpr_handle_t h, int i, float* ms);
 int mpr_search_plan(mpr_handle_t h, int b, int64_t n_local, int d, int kk, int* n_ctas, int* n_splits,
                     int* n_qtiles, int* n_stages, int* smem_bytes);
 
+/*
+ * The same planning WITHOUT a device (host-only; what the library would do on a GPU with `num_sms` SMs and default
+ * tuning): out[0] = CTAs, [1] = CTAs per q-tile, [2] = q-tiles, [3] = ring stages, [4] = dynamic shared memory bytes,
+ * [5] = queries per q-tile, [6] = 64-wide K sub-chunks per ring stage, [7] = epilogue groups, [8] = q-tile in tensor
+ * memory, [9] = hybrid q-tile, [10] = register lists, [11] = pending-candidate slots, [12] = rows of a q-tile slab in
+ * shared memory, [13] = workspace bytes (low 31 bits), [14] = threshold slots, [15] = replica words per slot.
+ * Lets the planner's invariants be tested on a machine without a GPU.
+ */
+int mpr_plan_host(int num_sms, int b, int64_t n_local, int d, int kk, int* out16);
+
 #ifdef __cplusplus
 }
 #endif

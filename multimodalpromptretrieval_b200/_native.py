@@ -21,7 +21,7 @@ STATUS_XCHG_TIMEOUT = 201
 EXPORTS = [
     "mpr_abi_version", "mpr_create", "mpr_destroy", "mpr_last_error", "mpr_device_error", "mpr_bank_build",
     "mpr_search_workspace_bytes", "mpr_search_topk", "mpr_merge_topk", "mpr_prompt_gather", "mpr_debug_scores",
-    "mpr_search_plan", "mpr_profile_begin", "mpr_profile_end", "mpr_profile_launch_ms", "mpr_exchange_bytes",
+    "mpr_search_plan", "mpr_plan_host", "mpr_profile_begin", "mpr_profile_end", "mpr_profile_launch_ms", "mpr_exchange_bytes",
     "mpr_search_fused_supported", "mpr_search_topk_fused", "mpr_retrieve", "mpr_retrieve_host",
     "mpr_set_exchange_timeout", "mpr_embed_prompt", "mpr_last_launch_count", "mpr_debug_counters", "mpr_debug_timeline", "mpr_debug_launch_ring", "mpr_retrieve_join", "mpr_workspace_invalidate",
     "mpr_token_cache_create", "mpr_token_cache_destroy", "mpr_token_cache_size", "mpr_token_cache_clear",
@@ -99,6 +99,8 @@ def load() -> C.CDLL:
                                       vp, vp, vp, vp, vp, vp, vp, vp]
     lib.mpr_debug_scores.restype = i32
     lib.mpr_debug_scores.argtypes = [vp, vp, i32, vp, vp, i64, i32, vp, vp, sz, vp]
+    lib.mpr_plan_host.restype = i32
+    lib.mpr_plan_host.argtypes = [i32, i32, i64, i32, i32, C.POINTER(i32)]
     lib.mpr_search_plan.restype = i32
     lib.mpr_search_plan.argtypes = [vp, i32, i64, i32, i32] + [C.POINTER(i32)] * 5
     lib.mpr_profile_begin.restype = i32

@@ -796,6 +796,25 @@ int mpr_search_plan(mpr_handle_t h, int b, int64_t n_local, int d, int kk, int* 
     return MPR_OK;
 }
 
+int mpr_plan_host(int num_sms, int b, int64_t n_local, int d, int kk, int* out16) {
+    if (!out16 || num_sms < 1) return fail(nullptr, MPR_EINVAL, "bad argument");
+    mpr_context ctx;                 // default tuning, no device
+    ctx.num_sms = num_sms;
+    ScanPlan pl;
+    const int rc = make_plan(&ctx, b, n_local, d, kk, &pl);
+    if (rc) {
+        strncpy(g_err, ctx.err, sizeof(g_err) - 1);
+        return rc;
+    }
+    const WsLayout wl = ws_layout(&ctx, pl, b, kk);
+    const int v[16] = {pl.n_splits * pl.n_qtiles, pl.n_splits, pl.n_qtiles, pl.n_stages, static_cast<int>(pl.smem_bytes),
+                       pl.q_tile, pl.sub_per_stage, pl.n_epi_groups, pl.q_tmem ? 1 : 0, pl.hybrid ? 1 : 0,
+                       pl.reg_list ? 1 : 0, pl.cand_cap, pl.q_box_rows, static_cast<int>(wl.total & 0x7FFFFFFF), wl.ns,
+                       1 << wl.rep_log2};
+    memcpy(out16, v, sizeof(v));
+    return MPR_OK;
+}
+
 int mpr_last_launch_count(mpr_handle_t h) { return h ? h->last_launches : 0; }
 
 int mpr_workspace_invalidate(mpr_handle_t h, const void* workspace) {

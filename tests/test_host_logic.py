@@ -171,6 +171,58 @@ def test_header_is_plain_c():
     assert res.returncode == 0, res.stderr
 
 
+PLAN_FIELDS = ("n_ctas", "n_splits", "n_qtiles", "n_stages", "smem_bytes", "q_tile", "sub_per_stage", "n_epi_groups", "q_tmem",
+               "hybrid", "reg_list", "cand_cap", "q_box_rows", "workspace_bytes", "ns", "replicas")
+
+
+def _plan(b, n, d, kk, sms=148):
+    lib = _native.load()
+    out = (ctypes.c_int32 * 16)()
+    rc = lib.mpr_plan_host(sms, b, n, d, kk, out)
+    return rc, dict(zip(PLAN_FIELDS, list(out)))
+
+
+def test_launch_planner_invariants_over_the_shape_space():
+    """The launch planner (csrc/mpr_abi.cu:make_plan) without a device: for every batch size / row width / list length the
+    reference or BASELINE.json can produce, the plan fits shared memory, keeps a usable ring, covers the batch, and picks
+    the q-tile placement the design describes."""
+    for d in (64, 128, 256, 512, 576, 640, 768, 1024, 1536, 2048):
+        for b in (1, 5, 16, 17, 33, 64, 65, 96, 128, 129, 200, 256, 300, 512, 1000, 4096):
+            for kk in (1, 2, 5, 6, 8, 9, 15, 16, 31, 32):
+                for n in (3, 3072, 1_250_000):
+                    rc, p = _plan(b, n, d, kk)
+                    assert rc == 0, (b, n, d, kk)
+                    assert p["smem_bytes"] <= 232448, (b, n, d, kk, p)
+                    assert p["n_stages"] >= 2 and p["sub_per_stage"] in (1, 2, 4)
+                    assert p["n_qtiles"] * p["q_tile"] >= b and (p["n_qtiles"] - 1) * p["q_tile"] < b
+                    assert 1 <= p["q_tile"] <= 128 and 1 <= p["n_splits"] and p["n_ctas"] == p["n_splits"] * p["n_qtiles"]
+                    assert p["n_splits"] <= max(1, -(-n // 128))                       # no CTA without a tile of its own
+                    assert p["reg_list"] == (1 if kk <= 8 else 0)
+                    assert p["ns"] >= kk and p["ns"] % 4 == 0 and p["ns"] * p["replicas"] <= (16 if kk <= 8 else 32)
+                    assert p["q_tmem"] == (1 if d <= 512 or p["hybrid"] else 0)
+                    if p["hybrid"]:
+                        assert 512 < d <= 1024 and b > 16 and p["n_stages"] >= 3
+                        assert p["q_box_rows"] % 16 == 0 and p["q_box_rows"] >= min(b, 128) or p["q_box_rows"] == 128
+                        assert (d // 64 - 8) * p["q_box_rows"] * 128 >= 32768           # room for the fill's scratch
+                    if d <= 512:
+                        assert p["q_box_rows"] == 0
+                    if 640 <= d <= 1024 and b > 16:
+                        assert p["hybrid"] == 1, (b, d, kk, p)
+                    if p["n_qtiles"] == 1 and n >= 128 * 148:
+                        assert p["n_ctas"] == 148                                        # one CTA per SM
+    # the headline shapes
+    rc, p = _plan(128, 10_000_000, 512, 5)
+    assert (p["n_ctas"], p["n_qtiles"], p["q_tmem"], p["reg_list"], p["replicas"]) == (148, 1, 1, 1, 2) and p["n_stages"] * p["sub_per_stage"] >= 8
+    rc, p = _plan(16, 1_062_912, 1024, 5)
+    assert (p["n_qtiles"], p["q_tmem"], p["hybrid"]) == (1, 0, 0)
+    rc, p = _plan(128, 1_000_000, 1024, 16)
+    assert (p["n_qtiles"], p["hybrid"], p["q_box_rows"], p["n_epi_groups"]) == (1, 1, 128, 1)
+    rc, p = _plan(4096, 1_048_576, 512, 5)
+    assert p["n_qtiles"] == 32 and p["n_ctas"] % 148 == 0
+    for bad in ((0, 100, 512, 5), (4, 100, 100, 5), (4, 100, 512, 33), (4, 100, 8192, 5)):
+        assert _plan(*bad)[0] != 0
+
+
 def test_ctypes_mirrors_match_the_header_structs(tmp_path):
     """``_native.RetrieveArgs`` / ``HostIO`` are written by hand next to ``mpr_retrieve_args`` / ``mpr_host_io``: size and
     every field offset must agree with what a C compiler makes of include/mpr_b200.h."""
