@@ -171,6 +171,50 @@ def test_header_is_plain_c():
     assert res.returncode == 0, res.stderr
 
 
+def test_shared_threshold_bound_never_drops_a_top_k_row():
+    """The exactness argument behind the scan's shared admission thresholds (csrc/scan_topk.cuh), replayed on the host:
+    lists cover disjoint rows; list (split, group) feeds word (slot * R + replica) with slot = (split + group * ns/2) % ns,
+    replica = (split // ns) % R; a slot's value is the maximum over its replicas; the bound is the minimum over the ns
+    slots.  Whatever subset of the lists has published so far, at least ns >= k+s distinct rows score >= the bound, so
+    the (k+s)-th best score is >= it and dropping rows STRICTLY below it keeps every top-(k+s) row, ties included."""
+    rng = np.random.default_rng(7)
+    for trial in range(300):
+        kk = int(rng.integers(1, 33))
+        ns = (kk + 3) & ~3
+        rep = 1
+        while rep < 4 and ns * rep * 2 <= (16 if kk <= 8 else 32):
+            rep *= 2
+        n_splits = int(rng.integers(ns, 149))
+        groups = int(rng.integers(1, 3))
+        rows_per_list = int(rng.integers(1, 40))
+        n_lists = n_splits * groups
+        # scores with many exact ties (few distinct values) in some trials
+        levels = int(rng.choice([3, 17, 10_000]))
+        scores = rng.integers(0, levels, size=(n_lists, rows_per_list)).astype(np.float64)
+        published = rng.random(n_lists) < rng.choice([0.3, 0.7, 1.0])            # lists that have published so far
+        words = np.full(ns * rep, -np.inf)
+        for l_ in range(n_lists):
+            if not published[l_]:
+                continue
+            split, grp = divmod(l_, groups)
+            slot = (split + grp * (ns // 2)) % ns
+            replica = (split // ns) % rep
+            # a list publishes the best score among the rows it has seen (any prefix of its rows is a valid state)
+            seen = int(rng.integers(1, rows_per_list + 1))
+            words[slot * rep + replica] = max(words[slot * rep + replica], scores[l_, :seen].max())
+        slot_val = words.reshape(ns, rep).max(axis=1)
+        if np.isinf(slot_val).any():
+            continue                                                             # some slot still empty: no bound yet
+        bound = slot_val.min()
+        flat = np.sort(scores.ravel())[::-1]
+        if flat.size < kk:
+            continue
+        kth = flat[kk - 1]
+        assert bound <= kth, (trial, kk, ns, rep)
+        assert (scores >= bound).sum() >= kk                                     # everything that can matter survives
+        assert not ((scores < bound) & (scores >= kth)).any()
+
+
 PLAN_FIELDS = ("n_ctas", "n_splits", "n_qtiles", "n_stages", "smem_bytes", "q_tile", "sub_per_stage", "n_epi_groups", "q_tmem",
                "hybrid", "reg_list", "cand_cap", "q_box_rows", "workspace_bytes", "ns", "replicas")
 
