@@ -588,12 +588,14 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 const int sd0 = kFuseQ ? p.qd0 : p.d, sd1 = kFuseQ ? p.qd1 : 0;
                 const int sdt = kFuseQ ? p.q_dtype : static_cast<int>(kSrcBF16);
                 float rs = 0.f;
-                // all 8 (16 for fp32) 128-bit loads of a chunk are issued before the first conversion: kWide is a
-                // compile-time constant so that the load loop has no branch the scheduler would not hoist loads across
-                auto fill_chunk = [&](auto wide_tag, int c) {
+                // all 8 (16 for fp32) 128-bit loads of a chunk are issued before the first conversion (kWide is a
+                // compile-time constant so that the load loop has no branch the scheduler would not hoist loads across),
+                // and the NEXT chunk's loads go out as soon as this chunk's registers are free — they are in flight while
+                // this chunk's rows are read back, squared and stored to tensor memory
+                uint4 raw[8][2];
+                bool ok[8];
+                auto load_chunk = [&](auto wide_tag, int c) {
                     constexpr bool kWide = decltype(wide_tag)::value;        // fp32 source: two 128-bit loads per unit
-                    uint4 raw[8][kWide ? 2 : 1];
-                    bool ok[8];
 #pragma unroll
                     for (int it = 0; it < 8; ++it) {
                         const int unit_idx = it * 32 + lane;
@@ -608,6 +610,9 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                         raw[it][0] = __ldg(src);
                         if constexpr (kWide) raw[it][1] = __ldg(src + 1);
                     }
+                };
+                auto store_chunk = [&](auto wide_tag) {
+                    constexpr bool kWide = decltype(wide_tag)::value;
 #pragma unroll
                     for (int it = 0; it < 8; ++it) {
                         const int unit_idx = it * 32 + lane;
@@ -641,10 +646,19 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                     }
                 };
                 const int n_tmem_chunks = min(p.n_chunks, kQTmemChunks);
+                const bool wide = sdt == kSrcF32;
+                if (grp < n_tmem_chunks) {
+                    if (wide) load_chunk(std::true_type{}, grp);
+                    else      load_chunk(std::false_type{}, grp);
+                }
                 for (int c = grp; c < n_tmem_chunks; c += kEpiGroups) {
-                    if (sdt == kSrcF32) fill_chunk(std::true_type{}, c);
-                    else                fill_chunk(std::false_type{}, c);
+                    if (wide) store_chunk(std::true_type{});
+                    else      store_chunk(std::false_type{});
                     __syncwarp();
+                    if (c + kEpiGroups < n_tmem_chunks) {
+                        if (wide) load_chunk(std::true_type{}, c + kEpiGroups);
+                        else      load_chunk(std::false_type{}, c + kEpiGroups);
+                    }
                     uint32_t w[32];
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
