@@ -212,7 +212,7 @@ __device__ __forceinline__ void store_merged(uint64_t elem, int q, int kk, int l
 // {high half | e << 32}: an aligned 8-byte store is single-copy atomic, so a reader that finds tag e in a word has that
 // word's payload — no fence, no separate flag, no second NVLink round trip (the flag + fence.sys protocol this replaces
 // cost a store round trip, a system fence and a flag round trip per step).  For query q a warp stores its kk keys into
-// word[e&1][my_rank] of EVERY rank's buffer (one 16-byte store per key and peer), then polls word[e&1][0..world) of its
+// word[e&3][my_rank] of EVERY rank's buffer (one 16-byte store per key and peer), then polls word[e&3][0..world) of its
 // OWN buffer until every word carries tag e and merges the world lists (keys are unique — they embed the global row — so
 // the merge is order-independent and ties still resolve to the lower row).  The last warp of the launch publishes
 // epoch = e.  Stale words carry an older tag (or 0) whatever batch shape wrote them.
