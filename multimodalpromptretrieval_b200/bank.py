@@ -116,6 +116,7 @@ class _Step:
         self.h_q = [None, None]                           # pinned staging for pageable host queries, per turn
         self.done_events = [torch.cuda.Event(), torch.cuda.Event()]   # submit(): "result block `turn` is on the host"
         self.in_flight = [False, False]                   # a submitted step still owns this turn's buffers
+        self._pinned_cache: Dict[tuple, bool] = {}
         self.stage_busy = [None, None]                    # event after a non-blocking step that read this turn's staging
         self.gen = [0, 0]                                 # submissions per turn (a stale handle must not release a newer step)
         # ---- argument blocks: everything that never changes is filled once
@@ -141,6 +142,19 @@ class _Step:
         self._tail_bound: Dict[bool, int] = {}
         self._bound_base = 0
         self.h_pre_np: list = []
+
+    def _is_pinned(self, t: torch.Tensor) -> bool:
+        """``Tensor.is_pinned`` asks the driver (~10-30 us); data loaders recycle their pinned buffers, so the answer is
+        remembered per (address, size).  A buffer freed and re-allocated pageable at the same address would be misjudged
+        only in the harmless direction of an extra lookup miss: entries are dropped when the table is full."""
+        key = (t.data_ptr(), t.numel() * t.element_size())
+        hit = self._pinned_cache.get(key)
+        if hit is None:
+            if len(self._pinned_cache) > 64:
+                self._pinned_cache.clear()
+            hit = bool(t.is_pinned())
+            self._pinned_cache[key] = hit
+        return hit
 
     def _views(self, block: torch.Tensor, stride: int) -> Dict[str, torch.Tensor]:
         b, kk, k = self.b, self.kk, self.k
@@ -215,7 +229,7 @@ class _Step:
             self.in_flight[turn] = False
         self._bind_turn(turn)
         if not img.is_cuda:
-            if not img.is_pinned():          # pageable host memory: stage through a pinned buffer of our own
+            if not self._is_pinned(img):     # pageable host memory: stage through a pinned buffer of our own
                 if self.h_q[turn] is None:
                     self.h_q[turn] = (torch.empty((self.b, self.d0), dtype=self.dtype).pin_memory(),
                                       torch.empty((self.b, self.d1), dtype=self.dtype).pin_memory() if self.d1 else None)
@@ -729,6 +743,8 @@ class RetrievalBank:
         st = self._step(img, txt, kk, skip)
         if self.exchange.world_size > 1 and self.exchange_mode == "nccl":
             return self._run_step_nccl(st, img, txt, prefix, use_quantifier, to_host)
+        if torch.cuda.current_device() == self.device.index and not K._NVTX:
+            return st.run(img, txt, prefix, use_quantifier, to_host, defer)       # hot path: no context managers
         with torch.cuda.device(self.device), K.nvtx_range("mpr.retrieval_step"):
             return st.run(img, txt, prefix, use_quantifier, to_host, defer)
 

@@ -36,6 +36,9 @@ class nvtx_range:
 
 
 def handle(device: Optional[int] = None) -> _native.Handle:
+    h = _handles.get(device) if device is not None else None      # hot path: one dict lookup
+    if h is not None:
+        return h
     if not torch.cuda.is_available():
         raise _native.NativeError("no CUDA device: this package runs on B200 (sm_100a) only and has no fallback path")
     if device is None:
@@ -54,6 +57,9 @@ def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
 def _stream(device=None) -> C.c_void_p:
     """The caller's current stream ON THE TENSORS' DEVICE (not on whatever device happens to be current); the library
     itself switches to its handle's device for the launch."""
+    if isinstance(device, torch.device) and device.index is not None:
+        # the raw handle of the current stream, without building a torch.cuda.Stream object (~10 us per step otherwise)
+        return C.c_void_p(torch._C._cuda_getCurrentRawStream(device.index))
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 

@@ -36,27 +36,54 @@ for i in range(8):
     bank.retrieve_prompt_ids_host(pool[i])
 
 
+EPOCH = 32          # the question set of an "epoch": these batches repeat, as a training set does
+
+
 def run(mode, lo, hi):
     t0 = time.perf_counter()
+    if mode == "epoch-two-deep":
+        bank.prefetch(pool[lo % EPOCH], True)
+        cur = bank.submit_prompt_ids_host(pool[lo % EPOCH])
+        bank.prefetch(pool[(lo + 1) % EPOCH], True)
+        for i in range(lo, hi):
+            bank.prefetch(pool[(i + 2) % EPOCH], True)
+            nxt = bank.submit_prompt_ids_host(pool[(i + 1) % EPOCH])
+            cur.result()
+            cur = nxt
+        cur.result()
+        return (time.perf_counter() - t0) / (hi - lo) * 1e6
     for i in range(lo, hi):
         if mode == "pipelined":
             bank.prefetch(pool[i + 1], True)
-        bank.retrieve_prompt_ids_host(pool[i] if mode != "repeated" else pool[i % 4])
+        if mode == "epoch-blocking":
+            bank.prefetch(pool[(i + 1) % EPOCH], True)
+            bank.retrieve_prompt_ids_host(pool[i % EPOCH])
+        else:
+            bank.retrieve_prompt_ids_host(pool[i] if mode != "repeated" else pool[i % 4])
     return (time.perf_counter() - t0) / (hi - lo) * 1e6
 
 
 out = io.StringIO()
-for mode in ("sequential", "pipelined", "repeated"):
+for mode in ("sequential", "pipelined", "repeated", "epoch-blocking", "epoch-two-deep"):
     if mode == "pipelined":
         bank.prefetch(pool[8], True)
+    if mode == "epoch-blocking":
+        for i in range(EPOCH):
+            bank.retrieve_prompt_ids_host(pool[i])          # the first epoch tokenises everything once
+        bank.prefetch(pool[8 % EPOCH], True)
     us = run(mode, 8, 8 + steps // 2)
     out.write(f"{mode}: {us:.1f} us per end-to-end step (bank {n} x {d}: GPU part ~40 us)\n")
 pr = cProfile.Profile()
 pr.enable()
-run("sequential", 8 + steps // 2, 8 + steps)
+if os.environ.get("PROFILE_MODE", "epoch-two-deep") == "epoch-blocking":
+    bank.prefetch(pool[(8 + steps // 2) % EPOCH], True)
+    run("epoch-blocking", 8 + steps // 2, 8 + steps)
+else:
+    run("epoch-two-deep", 8 + steps // 2, 8 + steps)
 pr.disable()
 st = pstats.Stats(pr, stream=out).sort_stats("cumulative")
-st.print_stats(28)
+st.print_stats(45)
+
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 open(os.path.join(ROOT, "gpurun_out", "host_profile.txt"), "w").write(out.getvalue())
-print(out.getvalue()[:6000])
+print(out.getvalue()[:14000])
