@@ -135,6 +135,7 @@ class ClockSampler:
     def __init__(self, gpu_index: int, period_ms: int = 2):
         self.samples, self.thread, self.proc, self._stop = [], None, None, False
         self.sm_max = None
+        self.active = True       # polled at full rate only around the regions whose clocks are reported (see run_native)
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -148,6 +149,9 @@ class ClockSampler:
 
             def poll():
                 while not self._stop:
+                    if not self.active:          # between the measured regions: stay out of the host path's way
+                        time.sleep(0.02)
+                        continue
                     try:
                         sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
                         pw = pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0
@@ -430,6 +434,8 @@ def run_native(args):
     # stream (mpr_profile_begin/end) so that the roofline speaks about the same K steps as `value`
     ms_step, (scan_ms, scan_n, scan_per), (t0, t1) = timed(device_step, args.steps, warm, profile=True)
     clocks = sampler.window(t0, t1) if sampler else None
+    if sampler:
+        sampler.active = False       # NVML polling every 2 ms competes with the host path measured next (GIL, driver locks)
     # ---- end to end: host inputs in (pinned embeddings + question STRINGS), host results out, every step
     # headline mode: the question set is finite and repeats every epoch (/root/reference/main.py:176-179), as in training;
     # an "epoch" here is EPOCH_BATCHES distinct batches (4096 distinct question strings at batch 128); the first pass over
@@ -492,6 +498,9 @@ def run_native(args):
     # sustained region: the same step for >= 0.6 s — a B200 under this load (HBM at full rate with the tensor pipe ~55 %
     # busy) settles at its 1 kW power cap with SM clocks near 1 GHz, which the ~30 ms region above never reaches
     steps_sus = args.steps if args.quick else min(4000, max(args.steps, int(math.ceil(600.0 / max(ms_step, 1e-3)))))
+    if sampler:
+        sampler.active = True
+        time.sleep(0.03)
     ms_sus, (sus_ms, sus_n, sus_per), (t2, t3) = timed(device_step, steps_sus, 3, profile=True)
     clocks_sus = sampler.window(t2, t3) if sampler else None
 
