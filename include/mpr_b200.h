@@ -148,7 +148,9 @@ int mpr_prompt_gather(mpr_handle_t h, const int32_t* idx, int b, int kk, int ski
  *
  * Queries: either raw halves q0 [b][d0] (|| q1 [b][d1]) of q_dtype (MPR_SRC_*) — prepared inside the scan kernel — or
  * q_bf16 [b][d] prepared earlier by mpr_bank_build (q0 == NULL).  q_scratch [b][d] bf16 is only needed for raw queries
- * with d > 512 and b > 128 (the kernel variant that shares bank tiles between CTA pairs takes prepared queries).
+ * that the scan cannot prepare itself: d > 1024 with several q-tiles (the variant that shares bank tiles between CTA
+ * pairs takes prepared queries) and normalised queries with 512 < d <= 1024 beyond 16 of them (hybrid q-tile); without
+ * it those shapes take a slower plan.
  * All pointers are device pointers owned by the caller; outputs may be NULL where noted.  The workspace
  * (mpr_search_workspace_bytes) belongs to ONE stream at a time; its control words are (re)zeroed by the library.
  * Sharded search (world > 1) is a COLLECTIVE: every rank must issue the same sequence of calls.

@@ -302,8 +302,9 @@ static int run_step(mpr_context* h, const mpr_retrieve_args& a, float* dump, cud
     ScanPlan pl;
     const int saved_reg = h->use_reg_list;
     if (kDump) h->use_reg_list = 0;            // the dump epilogue exists for the shared-memory-list variant only
-    // the hybrid q-tile takes prepared bf16 queries: raw ones go through kernel 1 into the caller's scratch first
-    const bool can_prepare = a.q0 == nullptr || a.q_scratch != nullptr;
+    // the hybrid q-tile takes prepared bf16 queries or raw ones that need no normalisation (the warps fill both halves);
+    // normalised raw queries go through kernel 1 into the caller's scratch first
+    const bool can_prepare = a.q0 == nullptr || a.q_scratch != nullptr || !a.normalise;
     int rc = make_plan(h, b, a.n_local, d, kk, &pl, !kDump && can_prepare);
     h->use_reg_list = saved_reg;
     if (rc) return rc;
@@ -317,7 +318,7 @@ static int run_step(mpr_context* h, const mpr_retrieve_args& a, float* dump, cud
     const uint16_t* q_bf16 = a.q_bf16;
     // tensor-bound regime with an even number of q-tiles: CTA pairs share each bank chunk by TMA multicast
     bool pair = !kDump && !pl.q_tmem && h->use_cluster && pl.n_qtiles >= 2 && pl.n_qtiles % 2 == 0;
-    if (raw && (pair || pl.hybrid)) {
+    if (raw && (pair || (pl.hybrid && a.normalise))) {
         if (a.q_scratch) {     // these variants take prepared queries: one kernel-1 launch into the caller's scratch
             const int threads = 256, rows_per_block = threads / 32;
             bank_build_kernel<<<(b + rows_per_block - 1) / rows_per_block, threads, 0, st>>>(
@@ -479,8 +480,10 @@ static int run_step(mpr_context* h, const mpr_retrieve_args& a, float* dump, cud
 #define MPR_LAUNCH(DUMP, CL, QT, FQ, RL, COOP) \
     launch_kernel(scan_topk_kernel<DUMP, CL, QT, FQ, RL>, grid, sm, st, CL, COOP, pdl, tq, tb, p, t)
     if (pl.hybrid) {
-        if (pl.reg_list) le = launch_kernel(scan_topk_kernel<false, 1, true, false, true, true>, grid, sm, st, 1, coop, pdl, tq, tb, p, t);
-        else             le = launch_kernel(scan_topk_kernel<false, 1, true, false, false, true>, grid, sm, st, 1, coop, pdl, tq, tb, p, t);
+        if (raw && pl.reg_list)  le = launch_kernel(scan_topk_kernel<false, 1, true, true, true, true>, grid, sm, st, 1, coop, pdl, tq, tb, p, t);
+        else if (raw)            le = launch_kernel(scan_topk_kernel<false, 1, true, true, false, true>, grid, sm, st, 1, coop, pdl, tq, tb, p, t);
+        else if (pl.reg_list)    le = launch_kernel(scan_topk_kernel<false, 1, true, false, true, true>, grid, sm, st, 1, coop, pdl, tq, tb, p, t);
+        else                     le = launch_kernel(scan_topk_kernel<false, 1, true, false, false, true>, grid, sm, st, 1, coop, pdl, tq, tb, p, t);
     } else if (pl.reg_list && !kDump) {
         if (pair)                     le = MPR_LAUNCH(false, 2, false, false, true, false);
         else if (pl.q_tmem && raw)    le = MPR_LAUNCH(false, 1, true, true, true, coop);
@@ -602,6 +605,8 @@ int mpr_create(int device, mpr_handle_t* out) {
     opt_in(scan_topk_kernel<false, 1, false, true, true>);
     opt_in(scan_topk_kernel<false, 1, true, false, true, true>);
     opt_in(scan_topk_kernel<false, 1, true, false, false, true>);
+    opt_in(scan_topk_kernel<false, 1, true, true, true, true>);
+    opt_in(scan_topk_kernel<false, 1, true, true, false, true>);
     {
         auto flag = [](const char* name) { const char* v = getenv(name); return v && v[0] == '1'; };
         if (flag("MPR_NO_CLUSTER")) h->use_cluster = 0;

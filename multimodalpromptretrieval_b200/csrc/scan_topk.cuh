@@ -130,7 +130,7 @@ __host__ __device__ inline ScanSmemLayout scan_smem_layout(int n_chunks /* of th
     l.bias_off = l.list_off + static_cast<uint32_t>(n_groups * kUmmaM) * scan_row_stride(kk_pad, cand_cap) * 8u;
     l.ring_off = l.bias_off + kAccBufs * kTileRows * 4u;
     l.scr_off = l.ring_off + kTileRing * 8u;
-    l.bar_off = l.scr_off + 2 * kUmmaM * 4u;
+    l.bar_off = l.scr_off + 3 * kUmmaM * 4u;
     l.total = l.bar_off + (2 + 2 * kMaxStages + 2 * kAccBufs) * 8u + 16u;
     return l;
 }
@@ -142,8 +142,10 @@ enum : int { kErrQFull = 101, kErrEmpty = 102, kErrFull = 103, kErrTmemEmpty = 1
 // One row of the query batch: concat + (normalise) + bf16 rounding exactly as kernel 1 does it (same per-lane
 // accumulation order and the same warp reduction, so `-0.5 * sum` equals kernel 1's bias bit for bit), written as 16-byte
 // units into a K-major SWIZZLE_128B shared-memory q-tile (slab j = K-chunk j, row r at r*128, unit c at (c ^ (r&7))*16).
+// `col_begin` (a multiple of 256): only columns >= col_begin are read and written, slab 0 = the chunk at col_begin
+// (the shared-memory half of a hybrid q-tile); normalisation needs the whole row and is not available with it.
 __device__ __forceinline__ float prep_query_row_to_smem(const ScanParams& p, long long src_row, bool real, uint8_t* q_tile,
-                                                        uint32_t slab_bytes, int r, int lane) {
+                                                        uint32_t slab_bytes, int r, int lane, int col_begin = 0) {
     const int steps = (p.d + 255) / 256;
     float x[kBuildMaxSteps][8];
     float ss = 0.f;
@@ -152,7 +154,7 @@ __device__ __forceinline__ float prep_query_row_to_smem(const ScanParams& p, lon
         const int col = s * 256 + lane * 8;
 #pragma unroll
         for (int i = 0; i < 8; ++i) x[s][i] = 0.f;
-        if (s < steps && col < p.d && real) {
+        if (s < steps && col < p.d && col >= col_begin && real) {
             if (col < p.qd0) load8(p.qsrc0, p.q_dtype, static_cast<size_t>(src_row) * p.qd0 + col, x[s]);
             else             load8(p.qsrc1, p.q_dtype, static_cast<size_t>(src_row) * p.qd1 + (col - p.qd0), x[s]);
 #pragma unroll
@@ -168,7 +170,7 @@ __device__ __forceinline__ float prep_query_row_to_smem(const ScanParams& p, lon
 #pragma unroll
     for (int s = 0; s < kBuildMaxSteps; ++s) {
         const int col = s * 256 + lane * 8;
-        if (s < steps && col < p.d) {
+        if (s < steps && col < p.d && col >= col_begin) {
             uint32_t packed[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -180,7 +182,7 @@ __device__ __forceinline__ float prep_query_row_to_smem(const ScanParams& p, lon
                 packed[i] = static_cast<uint32_t>(__bfloat16_as_ushort(lo)) |
                             (static_cast<uint32_t>(__bfloat16_as_ushort(hi)) << 16);
             }
-            const int unit = col >> 3, j = unit >> 3, c = unit & 7;
+            const int unit = (col - col_begin) >> 3, j = unit >> 3, c = unit & 7;
             *reinterpret_cast<uint4*>(q_tile + static_cast<size_t>(j) * slab_bytes + r * 128 + ((c ^ (r & 7)) << 4)) =
                 make_uint4(packed[0], packed[1], packed[2], packed[3]);
         }
@@ -200,7 +202,8 @@ __device__ __forceinline__ float prep_query_row_to_smem(const ScanParams& p, lon
 // only the pending buffer stays in shared memory.  Larger k keeps the list in shared memory as well.
 // kFuseQ: see ScanParams::qsrc0 — replaces /root/reference/dataset/VQAFeatureDataset.py:189-191 in-kernel, for the
 // tensor-memory q-tile (each epilogue thread converts its own row) and the shared-memory one (a warp per row, D <= 2048).
-// kHybrid (with kQTmem, prepared queries): K-chunks 8.. of the q-tile are an SS-mode A operand in shared memory.  A
+// kHybrid (with kQTmem): K-chunks 8.. of the q-tile are an SS-mode A operand in shared memory (brought in by TMA from
+// prepared queries, or written by the warps from raw ones with kFuseQ; normalised raw queries are prepared first).  A
 // compile-time switch because the MMA issue loop is issue-bound in the tensor-bound regime: a run-time branch per MMA
 // group cost cfg4 (4096 x 1 M x 512) 15 %.
 template <bool kDump, int kCluster, bool kQTmem, bool kFuseQ = false, bool kRegList = false, bool kHybrid = false>
@@ -250,7 +253,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     // ---- one-time setup
     if (threadIdx.x == 0) {
         ptx::mbar_init(bar_q, kWarpsFillQ ? 8 : 1);      // one arrive per epilogue warp, or the TMA producer's
-        if constexpr (kHybrid) ptx::mbar_init(bar_qs, 1);
+        if constexpr (kHybrid) ptx::mbar_init(bar_qs, kFuseQ ? 8 : 1);   // the producer's TMA, or one arrive per filling warp
         for (int s = 0; s < p.n_stages; ++s) {
             ptx::mbar_init(bar_full(s), 1);
             ptx::mbar_init(bar_empty(s), kCluster);      // one release per consumer CTA of the cluster
@@ -329,7 +332,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         // hybrid q-tile: K-chunks 8.. come in by TMA into shared memory whose first 32 KiB serve as the scratch of the
         // warps' tensor-memory fill — they are fetched once that fill is through (bar_q), right before the first bank
         // chunk that needs them is requested
-        bool q_smem_pending = kHybrid;
+        bool q_smem_pending = kHybrid && !kFuseQ;      // raw queries: the warps write the shared-memory half themselves
         // streamed bank: a ring stage holds up to sub_per_stage 64-wide K sub-chunks and costs ONE barrier round-trip
         const int spp = p.sub_per_stage;
         const uint32_t t_limit = dynamic ? static_cast<uint32_t>(p.n_tiles) : static_cast<uint32_t>(tile_end);
@@ -676,18 +679,35 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                     ptx::tmem_st_32x32b_x32(q_taddr + c * (kChunkK / 2), w);
                     __syncwarp();      // the scratch is rewritten by the next chunk
                 }
+                if constexpr (kFuseQ && kHybrid) {
+                    // raw queries beside a hybrid q-tile: once every warp is through with the scratch (it lives in the
+                    // shared-memory half), the eight warps write that half themselves, a warp per row (kernel 1's row
+                    // routine restricted to the columns beyond 512), and release it to the MMA warp
+                    ptx::named_bar_sync(5, 256);
+                    const uint32_t slab_bytes = static_cast<uint32_t>(p.q_box_rows) * 128u;
+                    for (int r = warp - 2; r < p.q_box_rows; r += 8) {
+                        const bool real = q0 + r < p.b_total && r < q_valid;
+                        const float rs2 = prep_query_row_to_smem(p, q0 + r, real, smem + lay.q_off, slab_bytes, r, lane,
+                                                                 kQTmemChunks * kChunkK);
+                        if (lane == 0 && r < kUmmaM) scratch[2 * kUmmaM + r] = real ? rs2 : 0.f;
+                    }
+                    ptx::fence_proxy_async_smem();       // generic-proxy stores -> visible to the tensor core's async proxy
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(bar_qs);
+                }
                 if constexpr (kFuseQ) {
                     if (split == 0 && p.q_bias_out) {                   // -0.5*|q|^2 for return_dists: the two halves meet here
                         scratch[grp * kUmmaM + row] = rs;
                         ptx::named_bar_sync(3, 256);
-                        if (grp == 0 && valid) p.q_bias_out[q0 + row] = -0.5f * (rs + scratch[kUmmaM + row]);
+                        if (grp == 0 && valid)
+                            p.q_bias_out[q0 + row] = -0.5f * (rs + scratch[kUmmaM + row] + (kHybrid ? scratch[2 * kUmmaM + row] : 0.f));
                     }
                 }
                 if constexpr (!kRegList) {
                     ptx::named_bar_sync(4, 256);       // every warp is through with its scratch: the memory becomes lists
                     if (active_group) for (int i = 0; i < kk; ++i) my_list[i] = 0ull;
                 }
-                if constexpr (kHybrid) ptx::fence_proxy_async_smem();   // scratch accesses before the TMA that overwrites it
+                if constexpr (kHybrid && !kFuseQ) ptx::fence_proxy_async_smem();   // scratch accesses before the TMA that overwrites it
             } else if constexpr (kFuseQ) {
                 auto load_q8 = [&](int col, float (&x)[8]) {      // 8 consecutive elements of [src0 | src1]
                     if (col < p.qd0) load8(p.qsrc0, p.q_dtype, qrow_idx * p.qd0 + col, x);

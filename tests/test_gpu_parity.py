@@ -612,8 +612,10 @@ def test_fused_query_cast_is_bit_identical_to_two_step(K, dtype, b, d0, d1, kk):
     keys, score, idx, qb = K.search_topk_fused(a, t, bank, bias, kk, idx_base=7)
     assert torch.equal(keys, keys_ref) and torch.equal(idx, idx_ref) and torch.equal(score, score_ref)
     assert (qb - qbias).abs().max().item() < 1e-3
-    if d > 512:
+    if d > 1024 or (d > 512 and b <= 16):
         assert torch.equal(qb, qbias)          # the shared-memory q-tile is filled by kernel 1's own row routine
+    if 512 < d <= 1024 and b > 16:             # hybrid q-tile, both halves filled from the raw rows in the one launch
+        assert K.last_launch_count() == 1 and K.search_plan(b, n, d, kk)["n_qtiles"] == -(-b // 128)
     assert K.handle(0).device_error() == 0
 
 
@@ -633,9 +635,9 @@ def test_fused_query_cast_with_normalise(K):
 
 
 def test_bank_step_with_raw_queries_on_the_hybrid_qtile(tokenizer):
-    """The reference's own row width (512 + 512) with a batch beyond 64 queries: the step prepares the raw halves with
-    kernel 1 into its scratch and scans with the hybrid q-tile; keys equal the two-step search on prepared queries, from
-    device-resident and from host-resident halves alike."""
+    """The reference's own row width (512 + 512) with a batch beyond 16 queries: the step scans with the hybrid q-tile,
+    both halves of which the kernel fills from the raw CLIP halves itself (one launch); keys equal the two-step search on
+    prepared queries, from device-resident and from host-resident halves alike."""
     from multimodalpromptretrieval_b200 import kernels as KK
     from multimodalpromptretrieval_b200.bank import RetrievalBank
     n, b, k = 7000, 100, 5
@@ -650,6 +652,7 @@ def test_bank_step_with_raw_queries_on_the_hybrid_qtile(tokenizer):
     q_prepared, _ = KK.bank_build(qi.to(dev()), qt.to(dev()))
     want, _, _ = KK.search_topk(q_prepared, bank.retrieval_embeddings, bank.bias, k)
     got_dev = bank.run_step(qi.to(dev()), qt.to(dev()), None, True, False)["device"]["keys"].clone()
+    assert KK.last_launch_count() == 1                                      # raw halves, hybrid q-tile, ONE launch
     got_host = bank.run_step(qi.pin_memory(), qt.pin_memory(), None, True, True)["host"]["keys"].clone()
     assert torch.equal(got_dev, want) and torch.equal(got_host.to(dev()), want)
     assert (want.cpu().numpy().view(np.uint64) != 0).all()
